@@ -1,0 +1,533 @@
+"""Host-side mirror of the 2DECOMP&FFT API for the hot path, on top of the C ABI (include/d2d_b200.h).
+
+The reference is Fortran; this image has no Fortran compiler, so the drop-in Fortran shim ships as
+source (2decomp-fft_b200/fortran/) and this module is the executable mirror of the same interface:
+same names, argument meaning and error behaviour as
+
+    decomp_2d_init / decomp_2d_finalize            src/decomp_2d_init_fin.f90:15-226
+    decomp_info_init / decomp_info                  src/decomp_2d.f90:382-515, src/info.f90:19-47
+    transpose_x_to_y / y_to_z / z_to_y / y_to_x     src/transpose_*.f90
+    alloc_x / alloc_y / alloc_z                     src/alloc.f90:10-134 (device: src/alloc_dev.f90)
+    decomp_2d_fft_init / _3d / _finalize / _get_size  src/fft_common.f90:42-327, src/fft_cufft.f90:676-1170
+
+PyTorch is plumbing only (device memory + torch.distributed for the unique-id broadcast); every
+compute call goes through ctypes into libd2dfft_b200.so.  There is NO fallback: if the shared
+library is missing, importing any compute entry point raises.
+
+Arrays are torch CUDA tensors viewed in Fortran order: shape (n1, n2, n3) with strides (1, n1, n1*n2),
+as returned by alloc_x/alloc_y/alloc_z.
+
+Module-level state ("current decomposition", "current FFT engine") is thread-local, so that several
+ranks can live in one process as threads (d2d_group transport) -- the reference keeps the same state
+in module variables of one MPI process.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libd2dfft_b200.so")
+
+# src/decomp_2d_constants.f90:86-93
+DECOMP_2D_FFT_FORWARD = -1
+DECOMP_2D_FFT_BACKWARD = 1
+PHYSICAL_IN_X = 1
+PHYSICAL_IN_Z = 3
+D2D_F32, D2D_F64 = 0, 1
+X_TO_Y, Y_TO_Z, Z_TO_Y, Y_TO_X = 0, 1, 2, 3
+
+
+class Decomp2dError(RuntimeError):
+    """What decomp_2d_abort (src/decomp_2d_mpi.f90:145-191) reports: error code + message."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"2DECOMP&FFT ERROR - errorcode: {code}\nERROR MESSAGE: {msg}")
+        self.errorcode = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def lib():
+    """Load libd2dfft_b200.so (fails loudly when it was not built: there is no CPU/PyTorch fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no fallback path)")
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        l.d2d_last_error.restype = C.c_char_p
+        l.d2d_version.restype = C.c_char_p
+        l.d2d_ctx_stream.restype = C.c_void_p
+        l.d2d_ctx_launch_count.restype = C.c_int64
+        for name in ("d2d_transpose", ):
+            getattr(l, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        for name in ("d2d_transpose_x_to_y", "d2d_transpose_y_to_z", "d2d_transpose_z_to_y", "d2d_transpose_y_to_x"):
+            getattr(l, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.d2d_fft_3d_c2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.d2d_fft_3d_r2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_fft_3d_c2r.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_fft_3d_c2c_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.d2d_fft_3d_r2c_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_fft_3d_c2r_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_fft_c2c_1m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        l.d2d_fft_r2c_1m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.d2d_fft_c2r_1m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.d2d_ctx_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.d2d_ctx_create_in_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.d2d_ctx_destroy.argtypes = [C.c_void_p]
+        l.d2d_ctx_sync.argtypes = [C.c_void_p]
+        l.d2d_ctx_set_blocking.argtypes = [C.c_void_p, C.c_int]
+        l.d2d_ctx_stream.argtypes = [C.c_void_p]
+        l.d2d_ctx_launch_count.argtypes = [C.c_void_p]
+        l.d2d_ctx_profile.argtypes = [C.c_void_p, C.c_int]
+        l.d2d_ctx_profile_count.argtypes = [C.c_void_p]
+        l.d2d_ctx_profile_reset.argtypes = [C.c_void_p]
+        l.d2d_ctx_profile_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_ctx_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        l.d2d_group_create.argtypes = [C.c_void_p, C.c_int]
+        l.d2d_group_destroy.argtypes = [C.c_void_p]
+        l.d2d_decomp_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.d2d_decomp_create_for_rank.argtypes = [C.c_int] * 6 + [C.c_void_p]
+        l.d2d_decomp_destroy.argtypes = [C.c_void_p]
+        l.d2d_decomp_query.argtypes = [C.c_void_p] * 10
+        l.d2d_decomp_dist.argtypes = [C.c_void_p] * 5
+        l.d2d_decomp_counts.argtypes = [C.c_void_p] * 9
+        l.d2d_fft_plan_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.d2d_fft_plan_destroy.argtypes = [C.c_void_p]
+        l.d2d_fft_plan_ph.argtypes = [C.c_void_p, C.c_void_p]
+        l.d2d_fft_plan_sp.argtypes = [C.c_void_p, C.c_void_p]
+        l.d2d_fft_get_size.argtypes = [C.c_void_p] * 4
+        l.d2d_host_alloc_pinned.argtypes = [C.c_void_p, C.c_int64]
+        l.d2d_host_free.argtypes = [C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise Decomp2dError(status, lib().d2d_last_error().decode())
+
+
+def get_unique_id():
+    """ncclGetUniqueId on rank 0 (src/decomp_2d_nccl.f90:182-185); broadcast it yourself."""
+    buf = (C.c_ubyte * 128)()
+    _check(lib().d2d_get_unique_id(buf))
+    return bytes(buf)
+
+
+def best_2d_grid(nproc):
+    r, c = C.c_int(), C.c_int()
+    _check(lib().d2d_best_2d_grid(nproc, C.byref(r), C.byref(c)))
+    return r.value, c.value
+
+
+class DecompInfo:
+    """decomp_info (src/info.f90:19-47): xst/xen/xsz ... (1-based starts like the reference)."""
+
+    def __init__(self, handle, p_row, p_col, owned=True):
+        self._h = handle
+        self._owned = owned
+        l = lib()
+        a = [(C.c_int * 3)() for _ in range(9)]
+        _check(l.d2d_decomp_query(handle, *a))
+        (self.xst, self.xen, self.xsz, self.yst, self.yen, self.ysz, self.zst, self.zen, self.zsz) = [tuple(x) for x in a]
+        d = [(C.c_int * p_row)(), (C.c_int * p_row)(), (C.c_int * p_col)(), (C.c_int * p_col)()]
+        _check(l.d2d_decomp_dist(handle, *d))
+        self.x1dist, self.y1dist, self.y2dist, self.z2dist = [tuple(x) for x in d]
+        c = [(C.c_int64 * p_row)(), (C.c_int64 * p_row)(), (C.c_int64 * p_col)(), (C.c_int64 * p_col)(),
+             (C.c_int64 * p_row)(), (C.c_int64 * p_row)(), (C.c_int64 * p_col)(), (C.c_int64 * p_col)()]
+        _check(l.d2d_decomp_counts(handle, *c))
+        (self.x1cnts, self.y1cnts, self.y2cnts, self.z2cnts, self.x1disp, self.y1disp, self.y2disp, self.z2disp) = [tuple(x) for x in c]
+
+    @classmethod
+    def for_rank(cls, nx, ny, nz, p_row, p_col, rank):
+        """Host-only decomposition record of any rank (no device needed)."""
+        h = C.c_void_p()
+        _check(lib().d2d_decomp_create_for_rank(nx, ny, nz, p_row, p_col, rank, C.byref(h)))
+        return cls(h, p_row, p_col)
+
+    def finalize(self):
+        if self._h is not None and self._owned:
+            lib().d2d_decomp_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+
+class Group:
+    """In-process rank group (thread-per-rank transport, d2d_group_*)."""
+
+    def __init__(self, nranks):
+        self._h = C.c_void_p()
+        self.nranks = nranks
+        _check(lib().d2d_group_create(C.byref(self._h), nranks))
+
+    def destroy(self):
+        if self._h:
+            lib().d2d_group_destroy(self._h)
+            self._h = None
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dtype_code(t):
+    torch = _torch()
+    if t.dtype in (torch.float64, torch.complex128):
+        return D2D_F64
+    if t.dtype in (torch.float32, torch.complex64):
+        return D2D_F32
+    raise Decomp2dError(2, f"unsupported dtype {t.dtype}")
+
+
+def _check_pencil(t, shape, what):
+    if tuple(t.shape) != tuple(shape):
+        raise Decomp2dError(2, f"{what}: array shape {tuple(t.shape)} does not match the pencil {tuple(shape)}")
+    n1, n2, _ = shape
+    if t.numel() and tuple(t.stride()) != (1, n1, n1 * n2):
+        raise Decomp2dError(2, f"{what}: array must be Fortran-ordered (use alloc_x/alloc_y/alloc_z)")
+    if not t.is_cuda:
+        raise Decomp2dError(2, f"{what}: array must live on the device")
+
+
+class Decomp2d:
+    """One rank's library state: what decomp_2d_init sets up (src/decomp_2d_init_fin.f90:15-184)."""
+
+    def __init__(self, nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None):
+        torch = _torch()
+        l = lib()
+        if p_row <= 0 or p_col <= 0:  # auto-tuning mode (decomp_2d_init_fin.f90:55-77)
+            p_row, p_col = best_2d_grid(nranks)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = device
+        self._h = C.c_void_p()
+        if group is not None:
+            _check(l.d2d_ctx_create_in_group(C.byref(self._h), group._h, rank, p_row, p_col, device))
+        else:
+            idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+            _check(l.d2d_ctx_create(C.byref(self._h), idbuf, nranks, rank, p_row, p_col, device))
+        self.nrank, self.nproc = rank, nranks
+        self.dims = (p_row, p_col)
+        self.coord = (rank // p_col, rank % p_col)
+        self.nx_global, self.ny_global, self.nz_global = nx, ny, nz
+        self.decomp_main = self.decomp_info_init(nx, ny, nz)
+        d = self.decomp_main
+        self.xstart, self.xend, self.xsize = d.xst, d.xen, d.xsz
+        self.ystart, self.yend, self.ysize = d.yst, d.yen, d.ysz
+        self.zstart, self.zend, self.zsize = d.zst, d.zen, d.zsz
+
+    # decomp_info_init (src/decomp_2d.f90:382-490)
+    def decomp_info_init(self, nx, ny, nz):
+        h = C.c_void_p()
+        _check(lib().d2d_decomp_create(self._h, nx, ny, nz, C.byref(h)))
+        return DecompInfo(h, *self.dims)
+
+    # alloc_x / alloc_y / alloc_z (src/alloc.f90:10-134): pencil-shaped array, Fortran order
+    def _alloc(self, pencil, dtype, decomp):
+        torch = _torch()
+        d = decomp or self.decomp_main
+        n1, n2, n3 = (d.xsz, d.ysz, d.zsz)[pencil]
+        base = torch.zeros((n3, n2, n1), dtype=dtype, device=f"cuda:{self.device}")
+        return base.permute(2, 1, 0)
+
+    def alloc_x(self, dtype, decomp=None):
+        return self._alloc(0, dtype, decomp)
+
+    def alloc_y(self, dtype, decomp=None):
+        return self._alloc(1, dtype, decomp)
+
+    def alloc_z(self, dtype, decomp=None):
+        return self._alloc(2, dtype, decomp)
+
+    def _transpose(self, direction, src, dst, decomp):
+        d = decomp or self.decomp_main
+        sizes = (d.xsz, d.ysz, d.zsz)
+        _check_pencil(src, sizes[(0, 1, 2, 1)[direction]], "src")
+        _check_pencil(dst, sizes[(1, 2, 1, 0)[direction]], "dst")
+        if src.dtype != dst.dtype:
+            raise Decomp2dError(2, "src and dst must have the same type")
+        _check(lib().d2d_transpose(self._h, d._h, direction, _dtype_code(src), int(src.is_complex()), src.data_ptr(), dst.data_ptr()))
+
+    def transpose_x_to_y(self, src, dst, decomp=None):
+        self._transpose(X_TO_Y, src, dst, decomp)
+
+    def transpose_y_to_z(self, src, dst, decomp=None):
+        self._transpose(Y_TO_Z, src, dst, decomp)
+
+    def transpose_z_to_y(self, src, dst, decomp=None):
+        self._transpose(Z_TO_Y, src, dst, decomp)
+
+    def transpose_y_to_x(self, src, dst, decomp=None):
+        self._transpose(Y_TO_X, src, dst, decomp)
+
+    # bare batched 1-D transforms on a local array (c2c_1m_x/y/z ..., src/fft_cufft.f90:489-671)
+    def c2c_1m(self, a, axis, isign, out=None):
+        out = a if out is None else out
+        n1, n2, n3 = a.shape
+        _check(lib().d2d_fft_c2c_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr(), isign))
+        return out
+
+    def r2c_1m(self, a, out, axis):
+        n1, n2, n3 = a.shape
+        _check(lib().d2d_fft_r2c_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr()))
+        return out
+
+    def c2r_1m(self, a, out, axis):
+        n1, n2, n3 = out.shape
+        _check(lib().d2d_fft_c2r_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr()))
+        return out
+
+    def sync(self):
+        _check(lib().d2d_ctx_sync(self._h))
+
+    def set_blocking(self, flag):
+        _check(lib().d2d_ctx_set_blocking(self._h, int(flag)))
+
+    def stream(self):
+        return lib().d2d_ctx_stream(self._h)
+
+    def launch_count(self):
+        return lib().d2d_ctx_launch_count(self._h)
+
+    def profile(self, enable):
+        _check(lib().d2d_ctx_profile(self._h, int(enable)))
+
+    def profile_reset(self):
+        _check(lib().d2d_ctx_profile_reset(self._h))
+
+    def profile_read(self):
+        """{label: (total_ms, calls, bytes)} of the per-stage device timers."""
+        l = lib()
+        out = {}
+        for i in range(l.d2d_ctx_profile_count(self._h)):
+            label = C.create_string_buffer(64)
+            ms, calls, by = C.c_double(), C.c_int64(), C.c_double()
+            _check(l.d2d_ctx_profile_get(self._h, i, label, C.byref(ms), C.byref(calls), C.byref(by)))
+            out[label.value.decode()] = (ms.value, calls.value, by.value)
+        return out
+
+    # decomp_2d_finalize (src/decomp_2d_init_fin.f90:189-226)
+    def finalize(self):
+        if self._h:
+            if self.decomp_main is not None:
+                self.decomp_main.finalize()
+                self.decomp_main = None
+            lib().d2d_ctx_destroy(self._h)
+            self._h = None
+
+
+class Decomp2dFFTEngine:
+    """decomp_2d_fft_engine (src/fft_cufft.f90:37-61; init: src/fft_common.f90:141-242)."""
+
+    def __init__(self, d2d, pencil, nx=None, ny=None, nz=None, dtype=None, opt_inplace=False, opt_inplace_r2c=False,
+                 opt_inplace_c2r=False, opt_skip_XYZ_c2c=None):
+        torch = _torch()
+        if pencil not in (PHYSICAL_IN_X, PHYSICAL_IN_Z):
+            raise Decomp2dError(1, "Invalid value for format")
+        if opt_inplace_r2c or opt_inplace_c2r:
+            # src/fft_common.f90:177-182: only the fftw_f03 backend supports in-place r2c / c2r
+            raise Decomp2dError(1, "In-place r2c / c2r transforms are not supported by this backend")
+        self.d2d = d2d
+        self.format = pencil
+        self.nx_fft = d2d.nx_global if nx is None else nx
+        self.ny_fft = d2d.ny_global if ny is None else ny
+        self.nz_fft = d2d.nz_global if nz is None else nz
+        self.dtype = torch.float64 if dtype is None else dtype
+        self.inplace = bool(opt_inplace)
+        skip = list(opt_skip_XYZ_c2c) if opt_skip_XYZ_c2c is not None else [False] * 3
+        self.skip_x_c2c, self.skip_y_c2c, self.skip_z_c2c = [bool(s) for s in skip]
+        cskip = (C.c_int * 3)(*[int(bool(s)) for s in skip])
+        self._h = C.c_void_p()
+        code = D2D_F64 if self.dtype == torch.float64 else D2D_F32
+        _check(lib().d2d_fft_plan_create(d2d._h, pencil, self.nx_fft, self.ny_fft, self.nz_fft, code, int(self.inplace), cskip,
+                                         C.byref(self._h)))
+        h = C.c_void_p()
+        _check(lib().d2d_fft_plan_ph(self._h, C.byref(h)))
+        self.ph = DecompInfo(h, *d2d.dims, owned=False)
+        h = C.c_void_p()
+        _check(lib().d2d_fft_plan_sp(self._h, C.byref(h)))
+        self.sp = DecompInfo(h, *d2d.dims, owned=False)
+
+    @property
+    def real_dtype(self):
+        return self.dtype
+
+    @property
+    def complex_dtype(self):
+        torch = _torch()
+        return torch.complex128 if self.dtype == torch.float64 else torch.complex64
+
+    # decomp_2d_fft_get_size (src/fft_common.f90:311-327)
+    def get_size(self):
+        a = [(C.c_int * 3)() for _ in range(3)]
+        _check(lib().d2d_fft_get_size(self._h, *a))
+        return tuple(a[0]), tuple(a[1]), tuple(a[2])
+
+    def _pencils(self, isign=None):
+        fx = self.format == PHYSICAL_IN_X
+        return fx
+
+    # decomp_2d_fft_3d generic interface (src/fft_common.f90:31-38): (in_c,out_c,isign) | (in_r,out_c) | (in_c,out_r)
+    def fft_3d(self, inp, out, isign=None):
+        fx = self.format == PHYSICAL_IN_X
+        if inp.is_complex() and out.is_complex():
+            if isign not in (DECOMP_2D_FFT_FORWARD, DECOMP_2D_FFT_BACKWARD):
+                raise Decomp2dError(1, "c2c transforms need isign = DECOMP_2D_FFT_FORWARD / _BACKWARD")
+            xyz = (fx and isign == DECOMP_2D_FFT_FORWARD) or ((not fx) and isign == DECOMP_2D_FFT_BACKWARD)
+            _check_pencil(inp, self.ph.xsz if xyz else self.ph.zsz, "in")
+            _check_pencil(out, self.ph.zsz if xyz else self.ph.xsz, "out")
+            _check(lib().d2d_fft_3d_c2c(self._h, inp.data_ptr(), out.data_ptr(), isign))
+        elif (not inp.is_complex()) and out.is_complex():
+            _check_pencil(inp, self.ph.xsz if fx else self.ph.zsz, "in_r")
+            _check_pencil(out, self.sp.zsz if fx else self.sp.xsz, "out_c")
+            _check(lib().d2d_fft_3d_r2c(self._h, inp.data_ptr(), out.data_ptr()))
+        elif inp.is_complex() and not out.is_complex():
+            _check_pencil(inp, self.sp.zsz if fx else self.sp.xsz, "in_c")
+            _check_pencil(out, self.ph.xsz if fx else self.ph.zsz, "out_r")
+            _check(lib().d2d_fft_3d_c2r(self._h, inp.data_ptr(), out.data_ptr()))
+        else:
+            raise Decomp2dError(1, "real to real transforms are not part of decomp_2d_fft_3d")
+
+    # host-array variants (what `!$acc data copyin(in) copy(out)` does around the reference's calls)
+    def fft_3d_r2c_host(self, in_host_ptr, out_host_ptr):
+        _check(lib().d2d_fft_3d_r2c_host(self._h, in_host_ptr, out_host_ptr))
+
+    def fft_3d_c2r_host(self, in_host_ptr, out_host_ptr):
+        _check(lib().d2d_fft_3d_c2r_host(self._h, in_host_ptr, out_host_ptr))
+
+    def fft_3d_c2c_host(self, in_host_ptr, out_host_ptr, isign):
+        _check(lib().d2d_fft_3d_c2c_host(self._h, in_host_ptr, out_host_ptr, isign))
+
+    def fin(self):
+        if self._h:
+            lib().d2d_fft_plan_destroy(self._h)
+            self._h = None
+
+
+# ---- module-level API with the reference's names (thread-local "module variables") ----------------
+_state = threading.local()
+
+
+def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None):
+    _state.d2d = Decomp2d(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, unique_id=unique_id, device=device, group=group)
+    _state.engines = {}
+    _state.current = None
+    return _state.d2d
+
+
+def decomp_2d_init_from_torch_distributed(nx, ny, nz, p_row, p_col):
+    """decomp_2d_init for a torchrun job: the unique id travels through torch.distributed
+    (any backend), standing in for the MPI_Bcast of src/decomp_2d_nccl.f90:185."""
+    torch = _torch()
+    import torch.distributed as dist
+    rank, nranks = dist.get_rank(), dist.get_world_size()
+    obj = [get_unique_id() if rank == 0 else None]
+    if nranks > 1:
+        dist.broadcast_object_list(obj, src=0)
+    return decomp_2d_init(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, unique_id=obj[0], device=torch.cuda.current_device())
+
+
+def _cur():
+    d = getattr(_state, "d2d", None)
+    if d is None:
+        raise Decomp2dError(1, "decomp_2d_init has not been called")
+    return d
+
+
+def decomp_2d_finalize():
+    decomp_2d_fft_finalize()
+    _cur().finalize()
+    _state.d2d = None
+
+
+def get_decomp_info():
+    return _cur().decomp_main
+
+
+def transpose_x_to_y(src, dst, decomp=None):
+    _cur().transpose_x_to_y(src, dst, decomp)
+
+
+def transpose_y_to_z(src, dst, decomp=None):
+    _cur().transpose_y_to_z(src, dst, decomp)
+
+
+def transpose_z_to_y(src, dst, decomp=None):
+    _cur().transpose_z_to_y(src, dst, decomp)
+
+
+def transpose_y_to_x(src, dst, decomp=None):
+    _cur().transpose_y_to_x(src, dst, decomp)
+
+
+def alloc_x(dtype, decomp=None):
+    return _cur().alloc_x(dtype, decomp)
+
+
+def alloc_y(dtype, decomp=None):
+    return _cur().alloc_y(dtype, decomp)
+
+
+def alloc_z(dtype, decomp=None):
+    return _cur().alloc_z(dtype, decomp)
+
+
+def decomp_2d_fft_init(pencil=PHYSICAL_IN_X, nx=None, ny=None, nz=None, igrid=1, **opts):
+    """decomp_2d_fft_init, all four overloads (src/fft_common.f90:42-138)."""
+    eng = Decomp2dFFTEngine(_cur(), pencil, nx, ny, nz, **opts)
+    old = _state.engines.get(igrid)
+    if old is not None:
+        old.fin()
+    _state.engines[igrid] = eng
+    _state.current = eng
+    return eng
+
+
+def decomp_2d_fft_use_grid(igrid=1):
+    _state.current = _state.engines[igrid]
+    return _state.current
+
+
+def decomp_2d_fft_get_engine(igrid=1):
+    return _state.engines[igrid]
+
+
+def decomp_2d_fft_3d(inp, out, isign=None):
+    eng = getattr(_state, "current", None)
+    if eng is None:
+        raise Decomp2dError(1, "decomp_2d_fft_init has not been called")
+    eng.fft_3d(inp, out, isign)
+
+
+def decomp_2d_fft_get_size():
+    return _state.current.get_size()
+
+
+def decomp_2d_fft_get_ph():
+    return _state.current.ph
+
+
+def decomp_2d_fft_get_sp():
+    return _state.current.sp
+
+
+def decomp_2d_fft_get_format():
+    return _state.current.format
+
+
+def decomp_2d_fft_finalize():
+    for eng in getattr(_state, "engines", {}).values():
+        eng.fin()
+    _state.engines = {}
+    _state.current = None

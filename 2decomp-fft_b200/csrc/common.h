@@ -1,0 +1,174 @@
+// common.h -- internal types of libd2dfft_b200 (context, decomposition, transport, errors).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/d2d_b200.h"
+#include "fft_kernel.cuh"
+
+namespace d2d {
+
+struct Error : std::runtime_error {
+   int code;
+   Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+const std::string &get_last_error();
+
+#define D2D_STR2(x) #x
+#define D2D_STR(x) D2D_STR2(x)
+#define D2D_CHECK_CUDA(call)                                                                                           \
+   do {                                                                                                                \
+      cudaError_t e__ = (call);                                                                                        \
+      if (e__ != cudaSuccess)                                                                                          \
+         throw ::d2d::Error(1000 + (int)e__, std::string(__FILE__ ":" D2D_STR(__LINE__) " " #call ": ") +              \
+                                                 cudaGetErrorString(e__));                                             \
+   } while (0)
+#define D2D_REQUIRE(cond, msg)                                                                                         \
+   do {                                                                                                                \
+      if (!(cond)) throw ::d2d::Error(2, std::string(__FILE__ ":" D2D_STR(__LINE__) " ") + (msg));                     \
+   } while (0)
+
+constexpr int kMaxP = kMaxPieces; // max ranks along one side of the process grid
+
+// decomp_info (src/info.f90:19-47).  0-based starts internally; the C ABI converts to 1-based.
+struct Decomp {
+   int nx, ny, nz, p_row, p_col, rank, c1, c2;
+   int xst[3], xen[3], xsz[3], yst[3], yen[3], ysz[3], zst[3], zen[3], zsz[3];
+   int x1dist[kMaxP], y1dist[kMaxP], y2dist[kMaxP], z2dist[kMaxP];
+   int x1off[kMaxP + 1], y1off[kMaxP + 1], y2off[kMaxP + 1], z2off[kMaxP + 1]; // exclusive prefix sums of the dists
+   int64_t x1cnts[kMaxP], y1cnts[kMaxP], y2cnts[kMaxP], z2cnts[kMaxP];
+   int64_t x1disp[kMaxP], y1disp[kMaxP], y2disp[kMaxP], z2disp[kMaxP];
+   int64_t pencil_elems(int p) const
+   {
+      const int *s = p == 0 ? xsz : p == 1 ? ysz : zsz;
+      return (int64_t)s[0] * s[1] * s[2];
+   }
+   int64_t max_pencil() const { return std::max(pencil_elems(0), std::max(pencil_elems(1), pencil_elems(2))); }
+};
+void decomp_init(Decomp &d, int nx, int ny, int nz, int p_row, int p_col, int rank);
+void best_2d_grid(int nproc, int *p_row, int *p_col);
+
+// ---- exchange transports ------------------------------------------------------------------------
+struct PeerXfer {
+   int peer;           // global rank
+   const void *sendptr;
+   size_t sendbytes;
+   void *recvptr;
+   size_t recvbytes;
+};
+
+struct Transport {
+   virtual ~Transport() {}
+   virtual int kind() const = 0;
+   // all-to-all(v) among the listed peers (self excluded by the caller); stream-ordered where the
+   // transport allows it.
+   virtual void exchange(const std::vector<PeerXfer> &xf, cudaStream_t st) = 0;
+   virtual void barrier(cudaStream_t st) = 0;
+};
+
+Transport *make_nccl_transport(const unsigned char id[128], int nranks, int rank);
+void nccl_unique_id(unsigned char id[128]);
+struct Group;
+Group *group_create(int nranks);
+void group_destroy(Group *);
+Transport *make_local_transport(Group *g, int rank);
+
+struct ProfEntry {
+   std::string label;
+   double total_ms = 0;
+   int64_t calls = 0;
+   double bytes = 0;
+};
+
+struct Ctx {
+   int nranks = 1, rank = 0, p_row = 1, p_col = 1, c1 = 0, c2 = 0, device = 0;
+   cudaStream_t stream = nullptr;
+   std::unique_ptr<Transport> tr;
+   bool blocking = true;
+   int64_t launches = 0;
+   // grow-only work buffers (the reference's work1/work2 high-water mark, src/decomp_2d.f90:461-485)
+   void *work[3] = {nullptr, nullptr, nullptr};
+   size_t work_bytes[3] = {0, 0, 0};
+   // profiling
+   bool profiling = false;
+   std::vector<ProfEntry> prof;
+   struct Pending {
+      int idx;
+      cudaEvent_t a, b;
+   };
+   std::vector<Pending> pending;
+   std::vector<cudaEvent_t> event_pool;
+
+   void *reserve(int which, size_t bytes);
+   void prof_begin(const char *label, double bytes, Pending &p);
+   void prof_end(Pending &p);
+   void prof_flush();
+   int peer_rank_col(int m) const { return m * p_col + c2; } // COL communicator: same coord(2), index = coord(1)
+   int peer_rank_row(int m) const { return c1 * p_col + m; } // ROW communicator: same coord(1), index = coord(2)
+   void finish_call()
+   {
+      if (blocking) D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+   }
+   ~Ctx();
+};
+
+struct ProfScope {
+   Ctx *c;
+   Ctx::Pending p{};
+   bool on;
+   ProfScope(Ctx *ctx, const char *label, double bytes = 0) : c(ctx), on(ctx->profiling)
+   {
+      if (on) c->prof_begin(label, bytes, p);
+   }
+   ~ProfScope()
+   {
+      if (on) c->prof_end(p);
+   }
+};
+
+// ---- copy (pack / unpack) kernels ----------------------------------------------------------------
+struct CopyArgs {
+   PieceMap in, out;  // element units of `es` bytes
+   int ne, na, nb;    // extents of the index space (e: pieces axis, a, b)
+   int fast_is_a;     // 1: `a` is the unit-stride axis of both sides, 0: `e` is
+};
+void launch_copy(Ctx *ctx, const CopyArgs &c, int es);
+
+// ---- twiddles -----------------------------------------------------------------------------------
+const void *twiddles_for(int device, int n, int f64);
+void twiddles_release_all();
+
+inline int elem_size(int dtype, int is_complex) { return (dtype == D2D_F64 ? 8 : 4) * (is_complex ? 2 : 1); }
+
+// piece-map builders.  `es`-agnostic: element units.
+PieceMap natural_map(const Decomp &d, int pencil, void *ptr);
+// send-side map of the transpose leaving pencil `from` towards pencil `to`; the self block stays in `sendbuf`
+PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es);
+// recv-side map for pencil `to` fed from pencil `from`: peers' blocks in recvbuf, own block in sendbuf
+PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es);
+// the exchange itself (peers other than self); element size es
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es);
+int64_t send_total(const Decomp &d, int from, int to);
+int64_t recv_total(const Decomp &d, int from, int to);
+int comm_size(const Decomp &d, int from, int to);
+
+void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src, void *dst);
+
+} // namespace d2d
+
+struct d2d_ctx {
+   d2d::Ctx c;
+};
+struct d2d_decomp {
+   d2d::Decomp d;
+   d2d::Ctx *ctx;
+};

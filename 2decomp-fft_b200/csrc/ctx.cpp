@@ -1,0 +1,214 @@
+// ctx.cpp -- rank context (stream, work buffers, per-stage device timers), twiddle tables, the FFT
+// kernel registry and the in-process (thread-per-rank) transport.
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <tuple>
+#include <cstring>
+
+#include "common.h"
+#include "fft_registry.h"
+
+namespace d2d {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+const std::string &get_last_error() { return g_last_error; }
+
+// ---- registry ----------------------------------------------------------------------------------
+static std::vector<FftKernelInfo> &registry()
+{
+   static std::vector<FftKernelInfo> r;
+   return r;
+}
+void fft_register(const FftKernelInfo &k) { registry().push_back(k); }
+const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec)
+{
+   for (const auto &k : registry())
+      if (k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec) return &k;
+   return nullptr;
+}
+int fft_registry_size() { return (int)registry().size(); }
+const FftKernelInfo *fft_registry_at(int i) { return &registry()[i]; }
+
+// ---- twiddles: per-pass tables [r-1][q] = exp(-2 pi i r q / (Ns R)), q in [0,Ns) -----------------
+namespace {
+struct TwKey {
+   int device, n, f64;
+   bool operator<(const TwKey &o) const { return std::tie(device, n, f64) < std::tie(o.device, o.n, o.f64); }
+};
+std::mutex g_tw_mutex;
+std::map<TwKey, void *> g_tw;
+} // namespace
+
+const void *twiddles_for(int device, int n, int f64)
+{
+   std::lock_guard<std::mutex> lk(g_tw_mutex);
+   TwKey key{device, n, f64};
+   auto it = g_tw.find(key);
+   if (it != g_tw.end()) return it->second;
+   const FftKernelInfo *k = nullptr;
+   for (int i = 0; i < fft_registry_size(); i++)
+      if (fft_registry_at(i)->n == n && fft_registry_at(i)->f64 == f64) { k = fft_registry_at(i); break; }
+   D2D_REQUIRE(k != nullptr, "no FFT kernel compiled for this length");
+   const int total = std::max(1, k->tw_total);
+   std::vector<double> hd((size_t)2 * total, 0.0);
+   size_t pos = 0;
+   long long ns = 1;
+   for (int p = 0; p < k->npass; p++) {
+      const int R = k->radix[p];
+      if (p >= 1) {
+         for (int r = 1; r < R; r++)
+            for (long long q = 0; q < ns; q++) {
+               const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(r * q) / (long double)(ns * R);
+               hd[2 * pos] = (double)cosl(ang);
+               hd[2 * pos + 1] = (double)sinl(ang);
+               pos++;
+            }
+      }
+      ns *= R;
+   }
+   D2D_REQUIRE((int)pos == k->tw_total, "twiddle table size mismatch");
+   void *dptr = nullptr;
+   const size_t bytes = (size_t)total * (f64 ? 16 : 8);
+   D2D_CHECK_CUDA(cudaMalloc(&dptr, bytes));
+   if (f64) {
+      D2D_CHECK_CUDA(cudaMemcpy(dptr, hd.data(), bytes, cudaMemcpyHostToDevice));
+   } else {
+      std::vector<float> hf(hd.begin(), hd.end());
+      D2D_CHECK_CUDA(cudaMemcpy(dptr, hf.data(), bytes, cudaMemcpyHostToDevice));
+   }
+   g_tw[key] = dptr;
+   return dptr;
+}
+
+void twiddles_release_all()
+{
+   std::lock_guard<std::mutex> lk(g_tw_mutex);
+   for (auto &kv : g_tw) cudaFree(kv.second);
+   g_tw.clear();
+}
+
+// ---- context -------------------------------------------------------------------------------------
+void *Ctx::reserve(int which, size_t bytes)
+{
+   if (bytes > work_bytes[which]) {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+      if (work[which]) D2D_CHECK_CUDA(cudaFree(work[which]));
+      work[which] = nullptr;
+      work_bytes[which] = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&work[which], bytes));
+      work_bytes[which] = bytes;
+   }
+   return work[which];
+}
+
+void Ctx::prof_begin(const char *label, double bytes, Pending &p)
+{
+   int idx = -1;
+   for (size_t i = 0; i < prof.size(); i++)
+      if (prof[i].label == label) { idx = (int)i; break; }
+   if (idx < 0) {
+      prof.push_back(ProfEntry{label, 0, 0, 0});
+      idx = (int)prof.size() - 1;
+   }
+   prof[idx].bytes += bytes;
+   auto get_event = [&]() {
+      cudaEvent_t e;
+      if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }
+      else D2D_CHECK_CUDA(cudaEventCreate(&e));
+      return e;
+   };
+   p.idx = idx;
+   p.a = get_event();
+   p.b = get_event();
+   D2D_CHECK_CUDA(cudaEventRecord(p.a, stream));
+}
+void Ctx::prof_end(Pending &p)
+{
+   cudaEventRecord(p.b, stream);
+   pending.push_back(p);
+}
+void Ctx::prof_flush()
+{
+   if (pending.empty()) return;
+   D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+   for (auto &p : pending) {
+      float ms = 0;
+      D2D_CHECK_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+      prof[p.idx].total_ms += ms;
+      prof[p.idx].calls += 1;
+      event_pool.push_back(p.a);
+      event_pool.push_back(p.b);
+   }
+   pending.clear();
+}
+
+Ctx::~Ctx()
+{
+   cudaSetDevice(device);
+   if (stream) cudaStreamSynchronize(stream);
+   tr.reset();
+   for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+   for (auto e : event_pool) cudaEventDestroy(e);
+   for (int i = 0; i < 3; i++)
+      if (work[i]) cudaFree(work[i]);
+   if (stream) cudaStreamDestroy(stream);
+}
+
+// ---- in-process transport: one host thread per rank, exchange = device-to-device copies ----------
+struct Group {
+   int n;
+   std::mutex m;
+   std::condition_variable cv;
+   int waiting = 0;
+   long long generation = 0;
+   std::vector<std::vector<PeerXfer>> posted;
+   explicit Group(int n_) : n(n_), posted(n_) {}
+   void barrier()
+   {
+      std::unique_lock<std::mutex> lk(m);
+      const long long gen = generation;
+      if (++waiting == n) {
+         waiting = 0;
+         generation++;
+         cv.notify_all();
+      } else {
+         cv.wait(lk, [&] { return generation != gen; });
+      }
+   }
+};
+Group *group_create(int nranks) { return new Group(nranks); }
+void group_destroy(Group *g) { delete g; }
+
+namespace {
+struct LocalTransport : Transport {
+   Group *g;
+   int rank;
+   LocalTransport(Group *g_, int r) : g(g_), rank(r) {}
+   int kind() const override { return D2D_TRANSPORT_LOCAL; }
+   void exchange(const std::vector<PeerXfer> &xf, cudaStream_t st) override
+   {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(st)); // my send segments are complete
+      g->posted[rank] = xf;
+      g->barrier();
+      for (const auto &x : xf) {
+         const PeerXfer *src = nullptr;
+         for (const auto &y : g->posted[x.peer])
+            if (y.peer == rank) src = &y;
+         D2D_REQUIRE(src != nullptr && src->sendbytes == x.recvbytes, "local exchange: send/recv size mismatch");
+         if (x.recvbytes) D2D_CHECK_CUDA(cudaMemcpyAsync(x.recvptr, src->sendptr, x.recvbytes, cudaMemcpyDefault, st));
+      }
+      D2D_CHECK_CUDA(cudaStreamSynchronize(st));
+      g->barrier(); // peers may now overwrite their send buffers
+   }
+   void barrier(cudaStream_t st) override
+   {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(st));
+      g->barrier();
+   }
+};
+} // namespace
+Transport *make_local_transport(Group *g, int rank) { return new LocalTransport(g, rank); }
+
+} // namespace d2d

@@ -1,0 +1,179 @@
+// decomp.cpp -- 2-D pencil decomposition arithmetic and the all-to-all layouts derived from it.
+// Follows decomp_info_init (src/decomp_2d.f90:382-490): get_dist (:1112-1133) -> partition x3
+// (:413-418, :1016-1064) -> prepare_buffer (:1138-1183); rank -> coord as MPI_CART_CREATE without
+// reorder (src/decomp_2d_init_fin.f90:95-123).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+
+namespace d2d {
+
+// distribute (src/decomp_2d.f90:1070-1105): n/p each, the last n%p ranks get one more
+static void distribute(int n, int p, int *sz, int *off)
+{
+   const int base = n / p, nu = n - base * p, nl = p - nu;
+   off[0] = 0;
+   for (int i = 0; i < p; i++) {
+      sz[i] = base + (i >= nl ? 1 : 0);
+      off[i + 1] = off[i] + sz[i];
+   }
+}
+
+void decomp_init(Decomp &d, int nx, int ny, int nz, int p_row, int p_col, int rank)
+{
+   D2D_REQUIRE(p_row >= 1 && p_col >= 1 && p_row <= kMaxP && p_col <= kMaxP, "process grid side must be in 1..8");
+   D2D_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, "grid sizes must be positive");
+   // src/decomp_2d_init_fin.f90:43-45 / decomp_2d.f90:399-405: every rank must own at least one point
+   D2D_REQUIRE(std::min(nx, ny) >= p_row && std::min(ny, nz) >= p_col,
+               "Make sure that min(nx,ny) >= p_row and min(ny,nz) >= p_col");
+   std::memset(&d, 0, sizeof(d));
+   d.nx = nx; d.ny = ny; d.nz = nz; d.p_row = p_row; d.p_col = p_col; d.rank = rank;
+   d.c1 = rank / p_col; d.c2 = rank % p_col;
+   distribute(nx, p_row, d.x1dist, d.x1off);
+   distribute(ny, p_row, d.y1dist, d.y1off);
+   distribute(ny, p_col, d.y2dist, d.y2off);
+   distribute(nz, p_col, d.z2dist, d.z2off);
+   // X-pencil (nx, ny/p_row, nz/p_col); Y-pencil (nx/p_row, ny, nz/p_col); Z-pencil (nx/p_row, ny/p_col, nz)
+   d.xst[0] = 0;              d.xsz[0] = nx;
+   d.xst[1] = d.y1off[d.c1];  d.xsz[1] = d.y1dist[d.c1];
+   d.xst[2] = d.z2off[d.c2];  d.xsz[2] = d.z2dist[d.c2];
+   d.yst[0] = d.x1off[d.c1];  d.ysz[0] = d.x1dist[d.c1];
+   d.yst[1] = 0;              d.ysz[1] = ny;
+   d.yst[2] = d.z2off[d.c2];  d.ysz[2] = d.z2dist[d.c2];
+   d.zst[0] = d.x1off[d.c1];  d.zsz[0] = d.x1dist[d.c1];
+   d.zst[1] = d.y2off[d.c2];  d.zsz[1] = d.y2dist[d.c2];
+   d.zst[2] = 0;              d.zsz[2] = nz;
+   for (int i = 0; i < 3; i++) {
+      d.xen[i] = d.xst[i] + d.xsz[i] - 1;
+      d.yen[i] = d.yst[i] + d.ysz[i] - 1;
+      d.zen[i] = d.zst[i] + d.zsz[i] - 1;
+   }
+   for (int i = 0; i < p_row; i++) {
+      d.x1cnts[i] = (int64_t)d.x1dist[i] * d.xsz[1] * d.xsz[2];
+      d.y1cnts[i] = (int64_t)d.ysz[0] * d.y1dist[i] * d.ysz[2];
+      d.x1disp[i] = i ? d.x1disp[i - 1] + d.x1cnts[i - 1] : 0;
+      d.y1disp[i] = i ? d.y1disp[i - 1] + d.y1cnts[i - 1] : 0;
+   }
+   for (int i = 0; i < p_col; i++) {
+      d.y2cnts[i] = (int64_t)d.ysz[0] * d.y2dist[i] * d.ysz[2];
+      d.z2cnts[i] = (int64_t)d.zsz[0] * d.zsz[1] * d.z2dist[i];
+      d.y2disp[i] = i ? d.y2disp[i - 1] + d.y2cnts[i - 1] : 0;
+      d.z2disp[i] = i ? d.z2disp[i - 1] + d.z2cnts[i - 1] : 0;
+   }
+}
+
+// best_2d_grid (src/decomp_2d_init_fin.f90:270-300) on top of findfactor (src/factor.f90:17-54)
+void best_2d_grid(int nproc, int *p_row, int *p_col)
+{
+   std::vector<int> f;
+   const int m = (int)std::sqrt((double)nproc);
+   for (int i = 1; i <= m; i++)
+      if (nproc % i == 0) f.push_back(i);
+   const int nlow = (int)f.size();
+   const bool square = f[nlow - 1] * f[nlow - 1] == nproc;
+   for (int i = nlow - 1 - (square ? 1 : 0); i >= 0; i--) f.push_back(nproc / f[i]);
+   *p_col = f[f.size() / 2];
+   *p_row = nproc / *p_col;
+}
+
+// ---- all-to-all layouts (pos formulas of mem_split_* / mem_merge_*) ------------
+namespace {
+struct Side {
+   const int *dist, *off;
+   const int64_t *cnts, *disp;
+   int np;
+};
+// the dist/disp table used by pencil `pencil` when talking to pencil `other`
+Side side_of(const Decomp &d, int pencil, int other)
+{
+   if (pencil == 0) return {d.x1dist, d.x1off, d.x1cnts, d.x1disp, d.p_row};
+   if (pencil == 2) return {d.z2dist, d.z2off, d.z2cnts, d.z2disp, d.p_col};
+   if (other == 0) return {d.y1dist, d.y1off, d.y1cnts, d.y1disp, d.p_row};
+   return {d.y2dist, d.y2off, d.y2cnts, d.y2disp, d.p_col};
+}
+// pieces along the pencil's own axis, blocks at base + disp[m] (element size es)
+PieceMap pieces(const Decomp &d, int pencil, const Side &s, char *base, int es)
+{
+   PieceMap m{};
+   m.np = s.np;
+   const int *sz = pencil == 0 ? d.xsz : pencil == 1 ? d.ysz : d.zsz;
+   for (int p = 0; p < s.np; p++) {
+      m.e0[p] = s.off[p];
+      m.ptr[p] = base + (size_t)es * s.disp[p];
+      if (pencil == 0) { // X lines (j,k) flattened: ii + w (j + n2 k)   (transpose_x_to_y.f90:314, transpose_y_to_x.f90:432)
+         m.se[p] = 1; m.sa[p] = s.dist[p]; m.sb[p] = 0;
+      } else if (pencil == 1) { // Y lines (i,k): i + n1 (jj + h k)  (transpose_x_to_y.f90:432, y_to_x:314, y_to_z:418, z_to_y:536)
+         m.se[p] = sz[0]; m.sa[p] = 1; m.sb[p] = (long long)sz[0] * s.dist[p];
+      } else { // Z lines (i,j) flattened: i + n1 (j + n2 kk)  (transpose_y_to_z.f90:538, z_to_y:418)
+         m.se[p] = (long long)sz[0] * sz[1]; m.sa[p] = 1; m.sb[p] = 0;
+      }
+   }
+   m.e0[s.np] = s.off[s.np];
+   return m;
+}
+} // namespace
+
+int comm_size(const Decomp &d, int from, int to) { return (from == 0 || to == 0) ? d.p_row : d.p_col; }
+
+PieceMap natural_map(const Decomp &d, int pencil, void *ptr)
+{
+   PieceMap m{};
+   m.np = 1;
+   const int *sz = pencil == 0 ? d.xsz : pencil == 1 ? d.ysz : d.zsz;
+   m.e0[0] = 0;
+   m.e0[1] = sz[pencil];
+   m.ptr[0] = ptr;
+   if (pencil == 0) { m.se[0] = 1; m.sa[0] = sz[0]; m.sb[0] = 0; }
+   else if (pencil == 1) { m.se[0] = sz[0]; m.sa[0] = 1; m.sb[0] = (long long)sz[0] * sz[1]; }
+   else { m.se[0] = (long long)sz[0] * sz[1]; m.sa[0] = 1; m.sb[0] = 0; }
+   return m;
+}
+
+PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es)
+{
+   return pieces(d, from, side_of(d, from, to), (char *)sendbuf, es);
+}
+PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es)
+{
+   PieceMap m = pieces(d, to, side_of(d, to, from), (char *)recvbuf, es);
+   // the block this rank "sends to itself" is never moved: read it where the producer wrote it
+   const Side s = side_of(d, from, to);
+   const int me = (from == 0 || to == 0) ? d.c1 : d.c2;
+   m.ptr[me] = (char *)sendbuf + (size_t)es * s.disp[me];
+   return m;
+}
+
+int64_t send_total(const Decomp &d, int from, int /*to*/) { return d.pencil_elems(from); }
+int64_t recv_total(const Decomp &d, int /*from*/, int to) { return d.pencil_elems(to); }
+
+// all-to-all(v) with the peers of the row / column communicator (self excluded).
+// Replaces decomp_2d_nccl_alltoall_{col,row}_* (src/decomp_2d_nccl.f90:214-473) / MPI_ALLTOALLV.
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es)
+{
+   const bool col = (from == 0 || to == 0);
+   const int np = col ? d.p_row : d.p_col;
+   const int me = col ? d.c1 : d.c2;
+   if (np == 1) return;
+   D2D_REQUIRE(ctx->tr != nullptr, "context has no transport but the process grid has more than one rank");
+   const Side s = side_of(d, from, to), r = side_of(d, to, from);
+   std::vector<PeerXfer> xf;
+   double bytes = 0;
+   for (int k = 1; k < np; k++) {
+      const int m = (me + k) % np; // stagger the peers
+      PeerXfer x;
+      x.peer = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
+      x.sendptr = (const char *)sendbuf + (size_t)es * s.disp[m];
+      x.sendbytes = (size_t)es * s.cnts[m];
+      x.recvptr = (char *)recvbuf + (size_t)es * r.disp[m];
+      x.recvbytes = (size_t)es * r.cnts[m];
+      bytes += (double)x.sendbytes;
+      xf.push_back(x);
+   }
+   static const char *names[3][3] = {{"", "a2a_x_y", ""}, {"a2a_y_x", "", "a2a_y_z"}, {"", "a2a_z_y", ""}};
+   ProfScope ps(ctx, names[from][to], bytes);
+   ctx->tr->exchange(xf, ctx->stream);
+}
+
+} // namespace d2d

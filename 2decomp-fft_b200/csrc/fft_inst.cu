@@ -1,0 +1,87 @@
+// fft_inst.cu -- instantiates the FFT kernels for one (D2D_N, D2D_F64) pair; compiled once per
+// pair (see Makefile) so that the template-heavy code builds in parallel.
+#include "fft_registry.h"
+
+#ifndef D2D_N
+#error "compile with -DD2D_N=<transform length> -DD2D_F64=<0|1>"
+#endif
+
+namespace d2d {
+namespace {
+
+#if D2D_F64
+using real_t = double;
+#else
+using real_t = float;
+#endif
+using T2 = Vec2<real_t>::type;
+using P = Pow2Plan<D2D_N>;
+
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// ---- geometry (see DESIGN.md "kernel geometry") ------------------------------------------------
+constexpr int kTargetThreads = 256;
+constexpr int kMaxSmem = 128 * 1024;
+constexpr int kLineBytes = P::N * (int)sizeof(T2);
+// contiguous-line kernel: TX = 1, LY lines per block
+constexpr int LY_LINE = cmax(1, cmin(kTargetThreads / P::T, kMaxSmem / kLineBytes));
+// strided-tile kernel: TX adjacent lines so that one row of the tile is 64 B
+constexpr int TX_WANT = 64 / (int)sizeof(T2);
+constexpr int TX_TILE = cmax(1, cmin(TX_WANT, cmin(1024 / P::T, kMaxSmem / kLineBytes)));
+constexpr int LY_TILE = cmax(1, cmin(kTargetThreads / (TX_TILE * P::T), kMaxSmem / (kLineBytes * TX_TILE)));
+constexpr int PADK = 16;
+
+constexpr int minb_for(int threads) { return cmax(1, (D2D_F64 ? 512 : 768) / threads); }
+
+template <int TX, int LY, int MODE, bool PAIRVEC> struct Inst {
+   using G = KernelGeom<real_t, P, TX, LY, PADK>;
+   static constexpr int MINB = minb_for(G::threads);
+   static cudaError_t launch(const FftArgs &g, cudaStream_t st)
+   {
+      auto kern = fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB>;
+      static bool attr_done = false; // per-process; every device of this process runs the same binary
+      const size_t smem = G::needs_smem ? G::smem_bytes : 0;
+      if (!attr_done && smem > 48 * 1024) {
+         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+         if (e != cudaSuccess) return e;
+      }
+      attr_done = true;
+      const long long tiles = (long long)((g.na + TX - 1) / TX) * g.nb;
+      const long long blocks = (tiles + LY - 1) / LY;
+      if (blocks <= 0) return cudaSuccess;
+      if (blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+      kern<<<(unsigned)blocks, G::threads, smem, st>>>(g);
+      return cudaGetLastError();
+   }
+   static void reg(int kind)
+   {
+      using PI = PlanInfo<P>;
+      FftKernelInfo k{};
+      k.n = P::N; k.f64 = D2D_F64; k.kind = kind; k.mode = MODE; k.pairvec = PAIRVEC ? 1 : 0;
+      k.tx = TX; k.ly = LY; k.threads = G::threads; k.minb = MINB;
+      k.smem = G::needs_smem ? G::smem_bytes : 0;
+      k.tw_total = PI::tw_total; k.npass = PI::npass;
+      for (int p = 0; p < 4; p++) k.radix[p] = PI::radix(p);
+      k.func = (const void *)fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB>;
+      k.launch = &launch;
+      fft_register(k);
+   }
+};
+
+struct Registrar {
+   Registrar()
+   {
+      Inst<1, LY_LINE, MODE_C2C, false>::reg(KIND_LINE);
+      Inst<1, LY_LINE, MODE_R2C, false>::reg(KIND_LINE);
+      Inst<1, LY_LINE, MODE_C2R, false>::reg(KIND_LINE);
+      Inst<TX_TILE, LY_TILE, MODE_C2C, false>::reg(KIND_TILE);
+      Inst<TX_TILE, LY_TILE, MODE_R2C, true>::reg(KIND_TILE);
+      Inst<TX_TILE, LY_TILE, MODE_C2R, true>::reg(KIND_TILE);
+      Inst<TX_TILE, LY_TILE, MODE_R2C, false>::reg(KIND_TILE);
+      Inst<TX_TILE, LY_TILE, MODE_C2R, false>::reg(KIND_TILE);
+   }
+} registrar_instance;
+
+} // namespace
+} // namespace d2d

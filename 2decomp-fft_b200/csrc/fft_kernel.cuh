@@ -1,0 +1,459 @@
+// fft_kernel.cuh -- batched 1-D FFT kernels for sm_100a (B200), the compute core of the library.
+//
+// Replaces the cuFFT plans/executions of the reference's GPU backend
+// (src/fft_cufft.f90:73-258 plan builders, :489-671 c2c_1m_{x,y,z}, r2c_1m_{x,z}, c2r_1m_{x,z})
+// AND the pack/unpack passes of the transposes (mem_split_* / mem_merge_*, src/transpose_*.f90):
+// every kernel reads its lines through a piecewise-strided map and writes them through another, so
+// the producing FFT writes straight into the per-destination send segments and the consuming FFT
+// gathers straight from the receive segments.  No stand-alone pack/unpack sweep touches HBM.
+//
+// Algorithm: Stockham autosort, radix 16/8/4/2 butterflies held in registers (E elements per
+// thread), inter-pass exchange through padded shared memory, per-pass twiddle tables laid out
+// [r][q] (bank-conflict-free, L1-resident, read with ld.global.nc).  fp64 and fp32.
+// One thread block processes TX*LY lines: TX adjacent lines of the fastest batch axis (lanes run
+// along that axis first, so a strided pencil is read in TX*sizeof(complex) contiguous runs) times
+// LY tiles.  TX=1 is the contiguous (X-pencil) variant.
+//
+// Real transforms use the two-for-one trick: two real lines (a, a+1 of the fastest batch axis) are
+// transformed as one complex line and separated in the epilogue (r2c) / combined in the prologue
+// (c2r).  c2r ignores Im(bin 0) and Im(bin n/2), which is exactly the effect of the reference's
+// "c2c then take the real part" (src/fft_generic.f90:320-337).
+//
+// Direction: the butterflies implement the forward transform exp(-2 pi i jk/n)
+// (DECOMP_2D_FFT_FORWARD = -1, src/decomp_2d_constants.f90:86); backward = conj . forward . conj,
+// applied for free at load/store.  No normalisation in either direction, like the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace d2d {
+
+constexpr int kMaxPieces = 8;
+
+enum FftMode { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
+
+// Piecewise-strided view of the complex lines of one stage.  The transform axis e in [0,n) is cut
+// into `np` pieces [e0[m], e0[m+1]); element e of line (a,b) lives at
+//    ptr[m] + (e - e0[m])*se[m] + a*sa[m] + b*sb[m]        (in complex elements).
+// np == 1 is a plain strided pencil; np > 1 is a send/recv buffer in the reference's all-to-all
+// layout -- or the peers' buffers themselves.
+struct PieceMap {
+   int np;
+   int e0[kMaxPieces + 1];
+   void *ptr[kMaxPieces];
+   long long se[kMaxPieces], sa[kMaxPieces], sb[kMaxPieces];
+};
+
+struct FftArgs {
+   PieceMap in, out; // complex side(s).  R2C uses only `out`, C2R only `in`.
+   // real side (R2C input / C2R output): natural pencil, element e of real line ar at
+   //    rptr + e*rse + ar*rsa + b*rsb   (in real elements); complex line pair index a <-> ar = 2a, 2a+1
+   void *rptr;
+   long long rse, rsa, rsb;
+   int na, nb;         // batch extents: na = fastest batch axis (complex lines; pairs count for real modes = ceil(na_real/2))
+   int na_real;        // number of real lines along a (R2C/C2R)
+   int n;              // transform length (checked against the template)
+   int backward;       // 1: conj-in / conj-out (isign=+1), C2C only
+   int passthrough;    // 1: opt_skip_XYZ_c2c -- move data through the maps without transforming
+   const void *tw;     // twiddle tables of this n / dtype
+};
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) { return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// multiply by -i : (x,y) -> (y,-x)
+template <typename T2> __device__ __forceinline__ T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }
+
+template <typename T> struct Consts;
+template <> struct Consts<double> {
+   static constexpr double rsqrt2 = 0.70710678118654752440;
+   static constexpr double c8 = 0.92387953251128675613; // cos(pi/8)
+   static constexpr double s8 = 0.38268343236508977173; // sin(pi/8)
+};
+template <> struct Consts<float> {
+   static constexpr float rsqrt2 = 0.70710678118654752440f;
+   static constexpr float c8 = 0.92387953251128675613f;
+   static constexpr float s8 = 0.38268343236508977173f;
+};
+
+// ---- forward butterflies, in place on v[B], v[B+S], ... ; output r ends up at v[B + out_idx(r)*S]
+template <typename T, int R> struct Bfly;
+
+template <typename T> struct Bfly<T, 1> {
+   using T2 = typename Vec2<T>::type;
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *) {}
+   static constexpr int out_idx(int r) { return r; }
+};
+
+template <typename T> struct Bfly<T, 2> {
+   using T2 = typename Vec2<T>::type;
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   {
+      T2 a = v[B], b = v[B + S];
+      v[B] = cadd(a, b);
+      v[B + S] = csub(a, b);
+   }
+   static constexpr int out_idx(int r) { return r; }
+};
+
+template <typename T> struct Bfly<T, 4> {
+   using T2 = typename Vec2<T>::type;
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   {
+      T2 a0 = cadd(v[B], v[B + 2 * S]), a1 = csub(v[B], v[B + 2 * S]);
+      T2 a2 = cadd(v[B + S], v[B + 3 * S]), a3 = mul_mi(csub(v[B + S], v[B + 3 * S]));
+      v[B] = cadd(a0, a2);
+      v[B + S] = cadd(a1, a3);
+      v[B + 2 * S] = csub(a0, a2);
+      v[B + 3 * S] = csub(a1, a3);
+   }
+   static constexpr int out_idx(int r) { return r; }
+};
+
+template <typename T> struct Bfly<T, 8> {
+   using T2 = typename Vec2<T>::type;
+   // DIF split 2 x 4: X[2m] = DFT4(x_k + x_{k+4})[m], X[2m+1] = DFT4((x_k - x_{k+4}) W8^k)[m]
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   {
+      const T h = Consts<T>::rsqrt2;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+         T2 a = v[B + k * S], b = v[B + (k + 4) * S];
+         v[B + k * S] = cadd(a, b);
+         v[B + (k + 4) * S] = csub(a, b);
+      }
+      { // W8^1 = (1 - i)/sqrt2 ; W8^2 = -i ; W8^3 = (-1 - i)/sqrt2
+         T2 t = v[B + 5 * S];
+         v[B + 5 * S] = T2{(t.x + t.y) * h, (t.y - t.x) * h};
+         v[B + 6 * S] = mul_mi(v[B + 6 * S]);
+         t = v[B + 7 * S];
+         v[B + 7 * S] = T2{(t.y - t.x) * h, -(t.x + t.y) * h};
+      }
+      Bfly<T, 4>::template run<B, S>(v);
+      Bfly<T, 4>::template run<B + 4 * S, S>(v);
+   }
+   static constexpr int out_idx(int r) { return (r & 1) * 4 + (r >> 1); }
+};
+
+template <typename T> struct Bfly<T, 16> {
+   using T2 = typename Vec2<T>::type;
+   // 4 x 4: i = k + 4l, r = m + 4n : X[m+4n] = sum_k W4^{kn} W16^{km} [ sum_l x_{k+4l} W4^{lm} ]
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   {
+      const T h = Consts<T>::rsqrt2, c = Consts<T>::c8, s = Consts<T>::s8;
+      Bfly<T, 4>::template run<B, 4 * S>(v); // u_k[m] at v[B + (k + 4m) S]
+      Bfly<T, 4>::template run<B + S, 4 * S>(v);
+      Bfly<T, 4>::template run<B + 2 * S, 4 * S>(v);
+      Bfly<T, 4>::template run<B + 3 * S, 4 * S>(v);
+      // twiddles W16^{km}, W16^p = (cos(p pi/8), -sin(p pi/8))
+      // m = 1: k=1 W^1, k=2 W^2, k=3 W^3
+      v[B + 5 * S] = cmul(v[B + 5 * S], T2{c, -s});
+      {
+         T2 t = v[B + 6 * S];
+         v[B + 6 * S] = T2{(t.x + t.y) * h, (t.y - t.x) * h};
+      }
+      v[B + 7 * S] = cmul(v[B + 7 * S], T2{s, -c});
+      // m = 2: k=1 W^2, k=2 W^4 = -i, k=3 W^6 = (-1 - i)/sqrt2
+      {
+         T2 t = v[B + 9 * S];
+         v[B + 9 * S] = T2{(t.x + t.y) * h, (t.y - t.x) * h};
+         v[B + 10 * S] = mul_mi(v[B + 10 * S]);
+         t = v[B + 11 * S];
+         v[B + 11 * S] = T2{(t.y - t.x) * h, -(t.x + t.y) * h};
+      }
+      // m = 3: k=1 W^3 = (s, -c), k=2 W^6, k=3 W^9 = (-c, s)
+      v[B + 13 * S] = cmul(v[B + 13 * S], T2{s, -c});
+      {
+         T2 t = v[B + 14 * S];
+         v[B + 14 * S] = T2{(t.y - t.x) * h, -(t.x + t.y) * h};
+      }
+      v[B + 15 * S] = cmul(v[B + 15 * S], T2{-c, s});
+      Bfly<T, 4>::template run<B, S>(v); // X[m+4n] at v[B + (4m+n) S]
+      Bfly<T, 4>::template run<B + 4 * S, S>(v);
+      Bfly<T, 4>::template run<B + 8 * S, S>(v);
+      Bfly<T, 4>::template run<B + 12 * S, S>(v);
+   }
+   static constexpr int out_idx(int r) { return 4 * (r & 3) + (r >> 2); }
+};
+
+// ---- radix plans for power-of-two n: E elements per thread, T = n/E threads per line ------------
+template <int N> struct Pow2Plan;
+#define D2D_PLAN(N_, E_, A, B, C, D)                                                                                   \
+   template <> struct Pow2Plan<N_> {                                                                                   \
+      static constexpr int N = N_, E = E_, T = N_ / E_;                                                                \
+      static constexpr int R0 = A, R1 = B, R2 = C, R3 = D;                                                             \
+   };
+D2D_PLAN(2, 2, 2, 1, 1, 1)
+D2D_PLAN(4, 4, 4, 1, 1, 1)
+D2D_PLAN(8, 8, 8, 1, 1, 1)
+D2D_PLAN(16, 16, 16, 1, 1, 1)
+D2D_PLAN(32, 8, 8, 4, 1, 1)
+D2D_PLAN(64, 8, 8, 8, 1, 1)
+D2D_PLAN(128, 16, 16, 8, 1, 1)
+D2D_PLAN(256, 16, 16, 16, 1, 1)
+D2D_PLAN(512, 8, 8, 8, 8, 1)
+D2D_PLAN(1024, 16, 16, 16, 4, 1)
+D2D_PLAN(2048, 16, 16, 16, 8, 1)
+D2D_PLAN(4096, 16, 16, 16, 16, 1)
+D2D_PLAN(8192, 16, 16, 16, 16, 2)
+D2D_PLAN(16384, 16, 16, 16, 16, 4)
+#undef D2D_PLAN
+
+template <class P> struct PlanInfo {
+   static constexpr int radix(int p) { return p == 0 ? P::R0 : p == 1 ? P::R1 : p == 2 ? P::R2 : P::R3; }
+   static constexpr int npass = (P::R1 == 1) ? 1 : (P::R2 == 1) ? 2 : (P::R3 == 1) ? 3 : 4;
+   static constexpr int ns(int p) { return p == 0 ? 1 : ns(p - 1) * radix(p - 1); } // product of earlier radices
+   // offset (in complex elements) of the twiddle table of pass p (p >= 1): sum_{q=1}^{p-1} (R_q - 1) * Ns_q
+   static constexpr int tw_off(int p) { return p <= 1 ? 0 : tw_off(p - 1) + (radix(p - 1) - 1) * ns(p - 1); }
+   static constexpr int tw_total = tw_off(npass);
+};
+
+// shared-memory index of line position p: one padding element every PADK elements
+template <int PADK> __device__ __forceinline__ constexpr int padix(int p) { return PADK > 0 ? p + p / (PADK > 0 ? PADK : 1) : p; }
+
+template <typename T2> __device__ __forceinline__ T2 ldg_nc(const T2 *p);
+template <> __device__ __forceinline__ double2 ldg_nc<double2>(const double2 *p) { return __ldg(p); }
+template <> __device__ __forceinline__ float2 ldg_nc<float2>(const float2 *p) { return __ldg(p); }
+
+__device__ __forceinline__ long long piece_addr(const PieceMap &m, int e, long long a, long long b, int &pc)
+{
+   int p = 0;
+   if (m.np > 1) {
+#pragma unroll 1
+      while (p + 1 < m.np && e >= m.e0[p + 1]) p++;
+   }
+   pc = p;
+   return (long long)(e - m.e0[p]) * m.se[p] + a * m.sa[p] + b * m.sb[p];
+}
+
+template <typename T2> __device__ __forceinline__ T2 load_piece(const PieceMap &m, int e, long long a, long long b)
+{
+   int pc;
+   long long off = piece_addr(m, e, a, b, pc);
+   return reinterpret_cast<const T2 *>(m.ptr[pc])[off];
+}
+template <typename T2> __device__ __forceinline__ void store_piece(const PieceMap &m, int e, long long a, long long b, T2 val)
+{
+   int pc;
+   long long off = piece_addr(m, e, a, b, pc);
+   reinterpret_cast<T2 *>(m.ptr[pc])[off] = val;
+}
+
+// One Stockham pass PASS on the registers of one thread (all loops are compile-time).
+template <typename T, class P, int PASS, int TX, int PADK> struct PassOp {
+   using T2 = typename Vec2<T>::type;
+   using PI = PlanInfo<P>;
+   static constexpr int E = P::E, TPL = P::T, N = P::N;
+   static constexpr int R = PI::radix(PASS), NS = PI::ns(PASS), NB = E / R; // NB butterflies per thread
+
+   static __device__ __forceinline__ void twiddle(T2 *v, int j, const T2 *__restrict__ tw)
+   {
+      if (PASS == 0) return;
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+         const int q = (j + TPL * u) % NS;
+#pragma unroll
+         for (int r = 1; r < R; r++) {
+            T2 w = ldg_nc(tw + PI::tw_off(PASS) + (r - 1) * NS + q);
+            v[u + r * NB] = cmul(v[u + r * NB], w);
+         }
+      }
+   }
+   static __device__ __forceinline__ void butterflies(T2 *v)
+   {
+      run_b<0>(v);
+   }
+   template <int U> static __device__ __forceinline__ void run_b(T2 *v)
+   {
+      if constexpr (U < NB) {
+         Bfly<T, R>::template run<U, NB>(v);
+         run_b<U + 1>(v);
+      }
+   }
+   // scatter the outputs to shared memory at their Stockham positions
+   static __device__ __forceinline__ void scatter(const T2 *v, int j, T2 *lsm)
+   {
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+         const int jj = j + TPL * u;
+         const int base = (jj / NS) * (NS * R) + (jj % NS);
+#pragma unroll
+         for (int r = 0; r < R; r++) lsm[padix<PADK>(base + r * NS) * TX] = v[u + Bfly<T, R>::out_idx(r) * NB];
+      }
+   }
+   // last pass: put output slot s = u + r*NB into w[s] (compile-time permutation)
+   static __device__ __forceinline__ void unpermute(const T2 *v, T2 *w)
+   {
+#pragma unroll
+      for (int u = 0; u < NB; u++)
+#pragma unroll
+         for (int r = 0; r < R; r++) w[u + r * NB] = v[u + Bfly<T, R>::out_idx(r) * NB];
+   }
+};
+
+template <typename T, class P, int PASS, int TX, int PADK> struct RunPasses {
+   using T2 = typename Vec2<T>::type;
+   using PI = PlanInfo<P>;
+   static __device__ __forceinline__ void run(T2 *v, int j, T2 *lsm, const T2 *__restrict__ tw)
+   {
+      using Op = PassOp<T, P, PASS, TX, PADK>;
+      Op::twiddle(v, j, tw);
+      Op::butterflies(v);
+      if constexpr (PASS + 1 < PI::npass) {
+         if (PASS > 0) __syncthreads(); // WAR: everyone has read the previous exchange
+         Op::scatter(v, j, lsm);
+         __syncthreads();
+#pragma unroll
+         for (int s = 0; s < P::E; s++) v[s] = lsm[padix<PADK>(j + P::T * s) * TX];
+         RunPasses<T, P, PASS + 1, TX, PADK>::run(v, j, lsm, tw);
+      } else {
+         T2 w[P::E];
+         Op::unpermute(v, w);
+#pragma unroll
+         for (int s = 0; s < P::E; s++) v[s] = w[s];
+      }
+   }
+};
+
+template <typename T, class P, int TX, int LY, int PADK> struct KernelGeom {
+   using T2 = typename Vec2<T>::type;
+   static constexpr int threads = TX * LY * P::T;
+   static constexpr int line_sm = padix<PADK>(P::N - 1) + 1; // padded complex elements per line
+   static constexpr size_t smem_bytes = (size_t)line_sm * TX * LY * sizeof(T2);
+   static constexpr bool needs_smem = (PlanInfo<P>::npass > 1);
+};
+
+// The kernel.  MODE: C2C / R2C / C2R.  PAIRVEC: real pairs (2a,2a+1) are adjacent and 2*sizeof(T)
+// aligned in memory (rsa == 1, even row pitch): load/store them as one vector.
+template <typename T, class P, int TX, int LY, int PADK, int MODE, bool PAIRVEC, int MINB>
+__global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_constant__ FftArgs g)
+{
+   using T2 = typename Vec2<T>::type;
+   using G = KernelGeom<T, P, TX, LY, PADK>;
+   constexpr int N = P::N, E = P::E, TPL = P::T;
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   T2 *sm = reinterpret_cast<T2 *>(smem_raw);
+
+   const int tid = threadIdx.x;
+   const int tx = tid % TX;
+   const int j = (tid / TX) % TPL;
+   const int ly = tid / (TX * TPL);
+   const long long tile = (long long)blockIdx.x * LY + ly;
+   const int tiles_a = (g.na + TX - 1) / TX;
+   const long long b = tile / tiles_a;
+   const long long a = (tile % tiles_a) * TX + tx;
+   const bool valid = (b < g.nb) && (a < g.na);
+   T2 *lsm = sm + (size_t)ly * (G::line_sm * TX) + tx;
+   const T2 *__restrict__ tw = reinterpret_cast<const T2 *>(g.tw);
+
+   T2 v[E];
+
+   // ------------------------------------------------------------------ load
+   if constexpr (MODE == MODE_C2C) {
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+         T2 x = T2{0, 0};
+         if (valid) x = load_piece<T2>(g.in, j + TPL * s, a, b);
+         if (g.backward) x.y = -x.y;
+         v[s] = x;
+      }
+   } else if constexpr (MODE == MODE_R2C) {
+      const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
+      const bool v1 = valid && (2 * a + 1 < g.na_real);
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+         const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
+         T2 x = T2{0, 0};
+         if constexpr (PAIRVEC) {
+            if (valid) x = *reinterpret_cast<const T2 *>(rp + off);
+         } else {
+            if (valid) x.x = rp[off];
+            if (v1) x.y = rp[off + g.rsa];
+         }
+         v[s] = x;
+      }
+   } else { // C2R: build conj(Z), Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]), in shared memory
+      const bool v1 = valid && (2 * a + 1 < g.na_real);
+#pragma unroll
+      for (int s = 0; s <= E / 2; s++) {
+         const int k = j + TPL * s;
+         if (k <= N / 2 && (s < E / 2 || j == 0)) {
+            T2 A = T2{0, 0}, B = T2{0, 0};
+            if (valid) A = load_piece<T2>(g.in, k, 2 * a, b);
+            if (v1) B = load_piece<T2>(g.in, k, 2 * a + 1, b);
+            if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
+            if constexpr (G::needs_smem) {
+               lsm[padix<PADK>(k) * TX] = T2{A.x - B.y, -(A.y + B.x)};
+               if (k > 0 && 2 * k < N) lsm[padix<PADK>(N - k) * TX] = T2{A.x + B.y, A.y - B.x};
+            } else { // single-thread line (T == 1, j == 0, k == s): slots are the positions
+               v[s] = T2{A.x - B.y, -(A.y + B.x)};
+               if (s > 0 && 2 * s < N) v[(N - s) % E] = T2{A.x + B.y, A.y - B.x};
+            }
+         }
+      }
+      if constexpr (G::needs_smem) {
+         __syncthreads();
+#pragma unroll
+         for (int s = 0; s < E; s++) v[s] = lsm[padix<PADK>(j + TPL * s) * TX];
+         __syncthreads();
+      }
+   }
+
+   // ------------------------------------------------------------------ transform
+   if (!g.passthrough) RunPasses<T, P, 0, TX, PADK>::run(v, j, lsm, tw);
+
+   // ------------------------------------------------------------------ store
+   if constexpr (MODE == MODE_C2C) {
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+         T2 x = v[s];
+         if (g.backward) x.y = -x.y;
+         if (valid) store_piece<T2>(g.out, j + TPL * s, a, b, x);
+      }
+   } else if constexpr (MODE == MODE_C2R) {
+      T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
+      const bool v1 = valid && (2 * a + 1 < g.na_real);
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+         const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
+         if constexpr (PAIRVEC) {
+            if (valid) *reinterpret_cast<T2 *>(rp + off) = T2{v[s].x, -v[s].y};
+         } else {
+            if (valid) rp[off] = v[s].x;
+            if (v1) rp[off + g.rsa] = -v[s].y;
+         }
+      }
+   } else { // R2C: separate the two spectra.  A[k] = (Z[k] + conj Z[n-k])/2, B[k] = (Z[k] - conj Z[n-k])/(2i)
+      const bool v1 = valid && (2 * a + 1 < g.na_real);
+      if constexpr (G::needs_smem) {
+         __syncthreads();
+#pragma unroll
+         for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * TX] = v[s];
+         __syncthreads();
+      }
+#pragma unroll
+      for (int s = 0; s <= E / 2; s++) {
+         const int k = j + TPL * s;
+         if (k <= N / 2 && (s < E / 2 || j == 0)) {
+            T2 zk, zn;
+            zk = v[s]; // slot s holds Z[j + T s] = Z[k]
+            if constexpr (G::needs_smem) {
+               zn = lsm[padix<PADK>((N - k) % N) * TX];
+            } else { // T == 1: k == s
+               zn = v[(N - s) % N];
+            }
+            const T hf = (T)0.5;
+            T2 A = T2{(zk.x + zn.x) * hf, (zk.y - zn.y) * hf};
+            T2 B = T2{(zk.y + zn.y) * hf, (zn.x - zk.x) * hf};
+            if (valid) store_piece<T2>(g.out, k, 2 * a, b, A);
+            if (v1) store_piece<T2>(g.out, k, 2 * a + 1, b, B);
+         }
+      }
+   }
+}
+
+} // namespace d2d

@@ -1,0 +1,335 @@
+// fft_plan.cpp -- FFT plans and the 3-D drivers.
+// Replaces the engine / plan management of the cuFFT backend (src/fft_cufft.f90:37-61 engine type,
+// :263-431 init_fft_engine with its 12 cufft plans, :436-483 finalize/use) and the GPU 3-D drivers
+// fft_3d_c2c / fft_3d_r2c / fft_3d_c2r (src/fft_cufft.f90:676-790, 795-934, 939-1170; CPU twins in
+// src/fft_common_3d.f90).  Stage order and the dims==1 special cases follow those drivers; what
+// differs is the data path: each 1-D stage reads through a receive-layout piece map and writes
+// through a send-layout piece map, so the transposes shrink to the bare exchange.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+#include "fft_registry.h"
+
+namespace d2d {
+
+struct Plan {
+   Ctx *ctx;
+   int format, nx, ny, nz, f64, inplace;
+   int skip[3];
+   d2d_decomp ph, sp;
+   // device staging for the *_host entry points
+   void *stage_in = nullptr, *stage_out = nullptr;
+   size_t stage_in_bytes = 0, stage_out_bytes = 0;
+};
+
+static const int *pencil_size(const Decomp &d, int p) { return p == 0 ? d.xsz : p == 1 ? d.ysz : d.zsz; }
+
+// One batched 1-D stage along `pencil` of the complex-side decomp dc (real side: dr, R2C/C2R only).
+// This is c2c_1m_{x,y,z} / r2c_1m_{x,z} / c2r_1m_{x,z} (src/fft_cufft.f90:489-671) fused with the
+// neighbouring mem_split_* / mem_merge_* through the maps.
+static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc, const Decomp *dr, const PieceMap &in,
+                      const PieceMap &out, void *rptr, int backward, int passthrough)
+{
+   const int *cs = pencil_size(dc, pencil);
+   FftArgs g{};
+   g.in = in;
+   g.out = out;
+   g.backward = backward;
+   g.passthrough = passthrough;
+   int lines;
+   if (pencil == 0) { g.na = cs[1] * cs[2]; g.nb = 1; }
+   else if (pencil == 1) { g.na = cs[0]; g.nb = cs[2]; }
+   else { g.na = cs[0] * cs[1]; g.nb = 1; }
+   lines = g.na * g.nb;
+   int n = cs[pencil];
+   int pairvec = 0;
+   const int rs = f64 ? 8 : 4;
+   double bytes = 2.0 * (double)lines * n * 2 * rs;
+   if (mode != MODE_C2C) {
+      D2D_REQUIRE(dr != nullptr && (pencil == 0 || pencil == 2), "real transforms run along x or z only");
+      const int *rsz = pencil_size(*dr, pencil);
+      n = rsz[pencil];
+      D2D_REQUIRE(cs[pencil] == n / 2 + 1, "complex extent must be n/2+1 along the real-transform axis");
+      g.rptr = rptr;
+      g.na_real = g.na;
+      g.na = (g.na_real + 1) / 2;
+      if (pencil == 0) { g.rse = 1; g.rsa = n; g.rsb = 0; }
+      else {
+         g.rse = (long long)rsz[0] * rsz[1]; g.rsa = 1; g.rsb = 0;
+         pairvec = ((g.rse % 2) == 0 && ((uintptr_t)rptr % (2 * rs)) == 0) ? 1 : 0;
+      }
+      bytes = (double)lines * n * rs + (double)lines * (n / 2 + 1) * 2 * rs;
+   }
+   g.n = n;
+   if (lines == 0) return;
+   const int kind = pencil == 0 ? KIND_LINE : KIND_TILE;
+   const FftKernelInfo *k = fft_find(n, f64, kind, mode, pairvec);
+   D2D_REQUIRE(k != nullptr, "transform length " + std::to_string(n) + " is not supported by the compiled kernels");
+   g.tw = twiddles_for(ctx->device, n, f64);
+   static const char *axes = "xyz";
+   char label[32];
+   snprintf(label, sizeof(label), "fft_%s_%c", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil]);
+   ProfScope ps(ctx, label, bytes);
+   cudaError_t e = k->launch(g, ctx->stream);
+   if (e != cudaSuccess) throw Error(1000 + (int)e, std::string("FFT kernel launch failed: ") + cudaGetErrorString(e));
+   ctx->launches++;
+}
+
+struct StageDef {
+   int pencil, mode;
+};
+
+// Generic 3-stage chain.  `in`/`out` are the user arrays; exactly one of them is real for r2c/c2r.
+static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward,
+                      bool in_writable)
+{
+   Ctx *ctx = p.ctx;
+   const int es = p.f64 ? 16 : 8;
+   const bool final_complex = st[2].mode == MODE_C2C;
+   const size_t wbytes = (size_t)es * dc.max_pencil();
+   bool live[3] = {false, false, false}; // work buffers holding the current stage's input
+   auto pick = [&](int avoid) {
+      for (int i = 0; i < 3; i++)
+         if (!live[i] && i != avoid) return i;
+      D2D_REQUIRE(false, "internal: no free work buffer");
+      return -1;
+   };
+   PieceMap cur = natural_map(dc, st[0].pencil, in); // complex input map (unused for R2C)
+   void *cur_nat = (st[0].mode == MODE_C2C && in_writable) ? in : nullptr; // natural complex buffer we may overwrite
+   int cur_w = -1;                                                             // ... and its work-buffer index, if any
+   for (int s = 0; s < 3; s++) {
+      const int pen = st[s].pencil, mode = st[s].mode;
+      const bool last = (s == 2);
+      const bool exch = !last && comm_size(dc, pen, st[s + 1].pencil) > 1;
+      bool later_local = true;
+      for (int t = s; t < 2; t++) later_local = later_local && comm_size(dc, st[t].pencil, st[t + 1].pencil) == 1;
+      const int passthrough = (mode == MODE_C2C && p.skip[pen]) ? 1 : 0;
+      PieceMap om{};
+      void *rptr = nullptr;
+      void *dst_nat = nullptr;
+      int dst_w = -1, send_w = -1;
+      if (mode == MODE_R2C) rptr = in;
+      if (last) {
+         if (mode == MODE_C2R) rptr = out;
+         else { om = natural_map(dc, pen, out); dst_nat = out; }
+      } else if (exch) {
+         send_w = pick(-1);
+         om = send_map(dc, pen, st[s + 1].pencil, ctx->reserve(send_w, wbytes), es);
+      } else {
+         if (mode == MODE_C2C && cur_nat) { dst_nat = cur_nat; dst_w = cur_w; } // in place
+         else if (final_complex && later_local) dst_nat = out;
+         else { dst_w = pick(-1); dst_nat = ctx->reserve(dst_w, wbytes); }
+         om = natural_map(dc, pen, dst_nat);
+      }
+      const bool noop = passthrough && !exch && dst_nat && dst_nat == cur_nat;
+      if (!noop) run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough);
+      if (last) break;
+      const int nxt = st[s + 1].pencil;
+      if (exch) {
+         // the input buffers of this stage are free once it has run (stream order)
+         bool was[3] = {live[0], live[1], live[2]};
+         live[0] = live[1] = live[2] = false;
+         live[send_w] = true;
+         int recv_w = -1;
+         for (int i = 0; i < 3; i++)
+            if (was[i] && i != send_w) { recv_w = i; break; }
+         if (recv_w < 0) recv_w = pick(-1);
+         void *sb = ctx->work[send_w];
+         void *rb = ctx->reserve(recv_w, wbytes);
+         sb = ctx->work[send_w];
+         exchange(ctx, dc, pen, nxt, sb, rb, es);
+         live[recv_w] = true;
+         cur = recv_map(dc, pen, nxt, rb, sb, es);
+         cur_nat = nullptr;
+         cur_w = -1;
+      } else {
+         live[0] = live[1] = live[2] = false;
+         if (dst_w >= 0) live[dst_w] = true;
+         cur = natural_map(dc, nxt, dst_nat);
+         cur_nat = dst_nat;
+         cur_w = dst_w;
+      }
+   }
+}
+
+static void reserve_all(Plan &p)
+{
+   // grow the context's work buffers once, at plan time (never inside the timed path)
+   const int es = p.f64 ? 16 : 8;
+   const size_t wb = (size_t)es * std::max(p.sp.d.max_pencil(), p.ph.d.max_pencil());
+   const bool multi = p.ctx->nranks > 1;
+   p.ctx->reserve(0, wb);
+   if (multi) { p.ctx->reserve(1, wb); p.ctx->reserve(2, wb); }
+}
+
+Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])
+{
+   D2D_REQUIRE(format == D2D_PHYSICAL_IN_X || format == D2D_PHYSICAL_IN_Z, "format must be PHYSICAL_IN_X (1) or PHYSICAL_IN_Z (3)");
+   D2D_REQUIRE(dtype == D2D_F32 || dtype == D2D_F64, "dtype must be D2D_F32 or D2D_F64");
+   std::unique_ptr<Plan> p(new Plan());
+   p->ctx = ctx;
+   p->format = format; p->nx = nx; p->ny = ny; p->nz = nz;
+   p->f64 = dtype == D2D_F64; p->inplace = inplace;
+   for (int i = 0; i < 3; i++) p->skip[i] = skip ? (skip[i] != 0) : 0;
+   p->ph.ctx = ctx; p->sp.ctx = ctx;
+   decomp_init(p->ph.d, nx, ny, nz, ctx->p_row, ctx->p_col, ctx->rank);
+   // sp (src/fft_common.f90:210-216)
+   if (format == D2D_PHYSICAL_IN_X) decomp_init(p->sp.d, nx / 2 + 1, ny, nz, ctx->p_row, ctx->p_col, ctx->rank);
+   else decomp_init(p->sp.d, nx, ny, nz / 2 + 1, ctx->p_row, ctx->p_col, ctx->rank);
+   D2D_CHECK_CUDA(cudaSetDevice(ctx->device));
+   reserve_all(*p);
+   return p.release();
+}
+
+void plan_destroy(Plan *p)
+{
+   if (!p) return;
+   cudaSetDevice(p->ctx->device);
+   cudaStreamSynchronize(p->ctx->stream);
+   if (p->stage_in) cudaFree(p->stage_in);
+   if (p->stage_out) cudaFree(p->stage_out);
+   delete p;
+}
+
+const d2d_decomp *plan_ph(const Plan *p) { return &p->ph; }
+const d2d_decomp *plan_sp(const Plan *p) { return &p->sp; }
+
+// fft_3d_c2c (src/fft_cufft.f90:676-790): X-forward / Z-backward run x -> y -> z, the others z -> y -> x
+void fft_3d_c2c(Plan *p, void *in, void *out, int isign)
+{
+   D2D_REQUIRE(isign == D2D_FFT_FORWARD || isign == D2D_FFT_BACKWARD, "isign must be -1 or +1");
+   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ProfScope ps(p->ctx, "fft_c2c");
+   const bool xyz = (p->format == D2D_PHYSICAL_IN_X && isign == D2D_FFT_FORWARD) ||
+                    (p->format == D2D_PHYSICAL_IN_Z && isign == D2D_FFT_BACKWARD);
+   const StageDef a[3] = {{0, MODE_C2C}, {1, MODE_C2C}, {2, MODE_C2C}};
+   const StageDef b[3] = {{2, MODE_C2C}, {1, MODE_C2C}, {0, MODE_C2C}};
+   run_chain(*p, p->ph.d, nullptr, xyz ? a : b, in, out, isign == D2D_FFT_BACKWARD, p->inplace != 0);
+}
+
+// fft_3d_r2c (src/fft_cufft.f90:795-934)
+void fft_3d_r2c(Plan *p, const void *in_r, void *out_c)
+{
+   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ProfScope ps(p->ctx, "fft_r2c");
+   const StageDef x[3] = {{0, MODE_R2C}, {1, MODE_C2C}, {2, MODE_C2C}};
+   const StageDef z[3] = {{2, MODE_R2C}, {1, MODE_C2C}, {0, MODE_C2C}};
+   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, const_cast<void *>(in_r), out_c, 0, false);
+}
+
+// fft_3d_c2r (src/fft_cufft.f90:939-1170)
+void fft_3d_c2r(Plan *p, void *in_c, void *out_r)
+{
+   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ProfScope ps(p->ctx, "fft_c2r");
+   const StageDef x[3] = {{2, MODE_C2C}, {1, MODE_C2C}, {0, MODE_C2R}};
+   const StageDef z[3] = {{0, MODE_C2C}, {1, MODE_C2C}, {2, MODE_C2R}};
+   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, in_c, out_r, 1, p->inplace != 0);
+}
+
+// sizes (bytes) of the user arrays of a plan: [0] real physical, [1] complex spectral, [2] complex physical (c2c in), [3] complex c2c out
+static void plan_bytes(const Plan *p, size_t b[4], int isign)
+{
+   const int rs = p->f64 ? 8 : 4;
+   const bool fx = p->format == D2D_PHYSICAL_IN_X;
+   b[0] = (size_t)rs * p->ph.d.pencil_elems(fx ? 0 : 2);
+   b[1] = (size_t)2 * rs * p->sp.d.pencil_elems(fx ? 2 : 0);
+   const bool xyz = (fx && isign == D2D_FFT_FORWARD) || (!fx && isign == D2D_FFT_BACKWARD);
+   b[2] = (size_t)2 * rs * p->ph.d.pencil_elems(xyz ? 0 : 2);
+   b[3] = (size_t)2 * rs * p->ph.d.pencil_elems(xyz ? 2 : 0);
+}
+
+static void ensure_stage(Plan *p, size_t bi, size_t bo)
+{
+   if (bi > p->stage_in_bytes) {
+      if (p->stage_in) D2D_CHECK_CUDA(cudaFree(p->stage_in));
+      p->stage_in = nullptr; p->stage_in_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&p->stage_in, bi));
+      p->stage_in_bytes = bi;
+   }
+   if (bo > p->stage_out_bytes) {
+      if (p->stage_out) D2D_CHECK_CUDA(cudaFree(p->stage_out));
+      p->stage_out = nullptr; p->stage_out_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&p->stage_out, bo));
+      p->stage_out_bytes = bo;
+   }
+}
+
+void plan_reserve_host_staging(Plan *p)
+{
+   size_t b[4];
+   plan_bytes(p, b, D2D_FFT_FORWARD);
+   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ensure_stage(p, std::max(b[0], std::max(b[1], b[2])), std::max(b[0], std::max(b[1], b[3])));
+}
+
+void fft_3d_host(Plan *p, int which /*0 r2c, 1 c2r, 2 c2c*/, const void *in_h, void *out_h, int isign)
+{
+   size_t b[4];
+   plan_bytes(p, b, isign);
+   const size_t bi = which == 0 ? b[0] : which == 1 ? b[1] : b[2];
+   const size_t bo = which == 0 ? b[1] : which == 1 ? b[0] : b[3];
+   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ensure_stage(p, bi, bo);
+   cudaStream_t st = p->ctx->stream;
+   {
+      ProfScope ps(p->ctx, "h2d", (double)bi);
+      D2D_CHECK_CUDA(cudaMemcpyAsync(p->stage_in, in_h, bi, cudaMemcpyHostToDevice, st));
+   }
+   if (which == 0) fft_3d_r2c(p, p->stage_in, p->stage_out);
+   else if (which == 1) {
+      const int keep = p->inplace;
+      p->inplace = 1; // the staging copy may be clobbered
+      fft_3d_c2r(p, p->stage_in, p->stage_out);
+      p->inplace = keep;
+   } else {
+      const int keep = p->inplace;
+      p->inplace = 1;
+      fft_3d_c2c(p, p->stage_in, p->stage_out, isign);
+      p->inplace = keep;
+   }
+   {
+      ProfScope ps(p->ctx, "d2h", (double)bo);
+      D2D_CHECK_CUDA(cudaMemcpyAsync(out_h, p->stage_out, bo, cudaMemcpyDeviceToHost, st));
+   }
+   D2D_CHECK_CUDA(cudaStreamSynchronize(st)); // host results must be complete on return
+}
+
+void plan_get_size(const Plan *p, int istart[3], int iend[3], int isize[3])
+{
+   // decomp_2d_fft_get_size (src/fft_common.f90:311-327): Z-pencil of sp for PHYSICAL_IN_X, X-pencil for PHYSICAL_IN_Z
+   const Decomp &s = p->sp.d;
+   const bool fx = p->format == D2D_PHYSICAL_IN_X;
+   for (int i = 0; i < 3; i++) {
+      istart[i] = (fx ? s.zst[i] : s.xst[i]) + 1;
+      iend[i] = (fx ? s.zen[i] : s.xen[i]) + 1;
+      isize[i] = fx ? s.zsz[i] : s.xsz[i];
+   }
+}
+Ctx *plan_ctx(Plan *p) { return p->ctx; }
+
+// ---- bare batched 1-D transforms on one local array (c2c_1m_* / r2c_1m_* / c2r_1m_*) -------------
+void fft_1m(Ctx *ctx, int dtype, int mode, int axis, int n1, int n2, int n3, const void *in, void *out, int isign)
+{
+   D2D_REQUIRE(axis >= 0 && axis < 3, "axis must be 0, 1 or 2");
+   D2D_REQUIRE(dtype == D2D_F32 || dtype == D2D_F64, "dtype must be D2D_F32 or D2D_F64");
+   D2D_CHECK_CUDA(cudaSetDevice(ctx->device));
+   const int f64 = dtype == D2D_F64;
+   Decomp dr, dc;
+   decomp_init(dr, n1, n2, n3, 1, 1, 0);
+   if (mode == MODE_C2C) {
+      run_stage(ctx, f64, mode, axis, dr, nullptr, natural_map(dr, axis, const_cast<void *>(in)), natural_map(dr, axis, out), nullptr,
+                isign == D2D_FFT_BACKWARD, 0);
+      return;
+   }
+   D2D_REQUIRE(axis == 0 || axis == 2, "real transforms run along x or z only");
+   const int c1 = axis == 0 ? n1 / 2 + 1 : n1, c3 = axis == 2 ? n3 / 2 + 1 : n3;
+   decomp_init(dc, c1, n2, c3, 1, 1, 0);
+   if (mode == MODE_R2C)
+      run_stage(ctx, f64, mode, axis, dc, &dr, PieceMap{}, natural_map(dc, axis, out), const_cast<void *>(in), 0, 0);
+   else
+      run_stage(ctx, f64, mode, axis, dc, &dr, natural_map(dc, axis, const_cast<void *>(in)), PieceMap{}, out, 1, 0);
+}
+
+} // namespace d2d

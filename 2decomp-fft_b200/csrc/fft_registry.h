@@ -1,0 +1,28 @@
+// fft_registry.h -- host-side table of the compiled FFT kernel instantiations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "fft_kernel.cuh"
+
+namespace d2d {
+
+enum FftKind { KIND_LINE = 0 /* TX = 1, contiguous lines */, KIND_TILE = 1 /* TX > 1, strided lines */ };
+
+struct FftKernelInfo {
+   int n, f64, kind, mode, pairvec;
+   int tx, ly, threads, minb;
+   size_t smem;
+   int tw_total;                 // complex twiddle entries expected in FftArgs::tw
+   int npass, radix[4];
+   const void *func;             // for cudaFuncSetAttribute / occupancy queries
+   cudaError_t (*launch)(const FftArgs &, cudaStream_t);
+};
+
+void fft_register(const FftKernelInfo &);
+// exact lookup; nullptr if this (n, dtype, kind, mode, pairvec) was not compiled
+const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec);
+int fft_registry_size();
+const FftKernelInfo *fft_registry_at(int i);
+
+} // namespace d2d

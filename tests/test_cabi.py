@@ -1,0 +1,68 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/d2d_b200.h
+declares, and its host-only decomposition arithmetic equals the oracle's (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from util import ROOT, pkg
+
+
+def test_library_exports_every_declared_symbol():
+    p = pkg()
+    lib = p.lib()
+    hdr = open(os.path.join(ROOT, "include", "d2d_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(d2d_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.d2d_version()
+
+
+def test_kernel_registry_covers_bench_sizes():
+    p = pkg()
+    lib = p.lib()
+    n = lib.d2d_fft_kernel_count()
+    buf = ctypes.create_string_buffer(256)
+    desc = []
+    for i in range(n):
+        assert lib.d2d_fft_kernel_describe(i, buf, 256) == 0
+        desc.append(buf.value.decode())
+    for size in (64, 256, 512, 1024, 2048):
+        for ty in ("f64", "f32"):
+            for kind in ("line", "tile"):
+                for mode in ("c2c", "r2c", "c2r"):
+                    assert any(d.startswith(f"n={size} {ty} {kind} {mode}") for d in desc), (size, ty, kind, mode)
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (2, 4), (3, 2), (4, 2), (8, 1), (1, 8)])
+@pytest.mark.parametrize("shape", [(17, 13, 11), (64, 64, 64), (1024, 1024, 513), (257, 512, 512), (1025, 2048, 2048)])
+def test_decomp_matches_oracle(shape, grid):
+    """d2d_decomp_* vs decomp_info_init of the reference (via the oracle): sizes, dists, counts, displacements."""
+    p = pkg()
+    for r in range(grid[0] * grid[1]):
+        d = p.DecompInfo.for_rank(*shape, grid[0], grid[1], r)
+        o = orc.Decomp(*shape, grid[0], grid[1], r)
+        for name in ("xsz", "ysz", "zsz", "x1dist", "y1dist", "y2dist", "z2dist", "x1cnts", "y1cnts", "y2cnts", "z2cnts",
+                     "x1disp", "y1disp", "y2disp", "z2disp"):
+            assert tuple(getattr(d, name)) == tuple(getattr(o, name)), (name, r)
+        for a, b in (("xst", "xst"), ("yst", "yst"), ("zst", "zst"), ("xen", "xen"), ("yen", "yen"), ("zen", "zen")):
+            assert tuple(x - 1 for x in getattr(d, a)) == tuple(getattr(o, b)), (a, r)  # C ABI is 1-based
+        d.finalize()
+
+
+def test_best_2d_grid_matches_oracle():
+    p = pkg()
+    for n in (1, 2, 3, 4, 6, 8, 12, 16, 24, 36, 64):
+        assert p.best_2d_grid(n) == orc.best_2d_grid(n)
+
+
+def test_invalid_grid_reports_reference_error():
+    """decomp_2d_init_fin.f90:43-45: min(nx,ny) >= p_row and min(ny,nz) >= p_col, status + message, no abort."""
+    p = pkg()
+    with pytest.raises(p.Decomp2dError) as e:
+        p.DecompInfo.for_rank(4, 4, 4, 8, 1, 0)
+    assert "p_row" in str(e.value)
