@@ -412,6 +412,32 @@ int d2d_memcpy_async(d2d_ctx *ctx, void *dst, const void *src, int64_t bytes, in
 }
 
 int d2d_fft_kernel_count(void) { return fft_registry_size(); }
+int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int *np, int e0[9], int64_t off[8],
+                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb)
+{
+   D2D_TRY
+   D2D_REQUIRE((pencil == 1 && (other == 0 || other == 2)) || (other == 1 && (pencil == 0 || pencil == 2)), "not a link");
+   char *peers = reinterpret_cast<char *>(uintptr_t(1) << 44), *self = reinterpret_cast<char *>(uintptr_t(1) << 45);
+   const PieceMap m = fft_link_map(decomp->d, pencil, other, peers, self, 1, consumer != 0);
+   *np = m.np;
+   for (int p = 0; p <= m.np; p++) e0[p] = m.e0[p];
+   for (int p = 0; p < m.np; p++) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(m.ptr[p]);
+      in_self[p] = (a >> 45) & 1;
+      off[p] = (int64_t)(a & ((uintptr_t(1) << 44) - 1));
+      se[p] = m.se[p]; sa[p] = m.sa[p]; sb[p] = m.sb[p];
+   }
+   fft_stage_batch(decomp->d, pencil, *na, *nb);
+   D2D_CATCH
+}
+int d2d_debug_user_map(const d2d_decomp *decomp, int pencil, int64_t *se, int64_t *sa, int64_t *sb, int *n, int *na, int *nb)
+{
+   D2D_TRY
+   const PieceMap m = fft_user_map(decomp->d, pencil, nullptr);
+   *se = m.se[0]; *sa = m.sa[0]; *sb = m.sb[0]; *n = m.e0[1];
+   fft_stage_batch(decomp->d, pencil, *na, *nb);
+   D2D_CATCH
+}
 int d2d_fft_kernel_describe(int i, char *buf, int buflen)
 {
    if (i < 0 || i >= fft_registry_size()) return 1;

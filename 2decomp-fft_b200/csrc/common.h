@@ -160,6 +160,10 @@ void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, 
 int64_t send_total(const Decomp &d, int from, int to);
 int64_t recv_total(const Decomp &d, int from, int to);
 int comm_size(const Decomp &d, int from, int to);
+// private wire layouts of the fused 3-D transforms (decomp.cpp)
+void fft_stage_batch(const Decomp &d, int pencil, int &na, int &nb);
+PieceMap fft_user_map(const Decomp &d, int pencil, void *ptr);
+PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer);
 
 void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src, void *dst);
 

@@ -148,6 +148,70 @@ PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbu
 int64_t send_total(const Decomp &d, int from, int /*to*/) { return d.pencil_elems(from); }
 int64_t recv_total(const Decomp &d, int /*from*/, int to) { return d.pencil_elems(to); }
 
+// ---- private wire layouts of the fused 3-D transforms ---------------------------------------------
+// Only pencil contents are contractual: inside decomp_2d_fft_3d the blocks that
+// travel between ranks keep the reference's per-peer COUNTS and DISPLACEMENTS (so the exchange is the
+// same all-to-all-v) but are ordered INSIDE for the memory system:
+//     Z <-> Y link: block stored (z, y, x)   -- z fastest
+//     Y <-> X link: block stored (y, x, z)   -- y fastest
+// so that every stage either streams whole lines (its transform axis is the unit-stride axis) or
+// reads TX-wide tiles whose rows are only a few KB apart.  On B200 a tile whose rows are >= 1 MB
+// apart runs at ~1/2 the bandwidth (one 2 MB page per row; measured), which is what
+// the reference layouts (x fastest everywhere) force on the z stage.
+// Batch axes of a stage (a = the axis TX adjacent lines of a tile run along, b = the other one):
+//     X stage: a = y, b = z      Y stage: a = z, b = x      Z stage: a = x, b = y
+void fft_stage_batch(const Decomp &d, int pencil, int &na, int &nb)
+{
+   if (pencil == 0) { na = d.xsz[1]; nb = d.xsz[2]; }
+   else if (pencil == 1) { na = d.ysz[2]; nb = d.ysz[0]; }
+   else { na = d.zsz[0]; nb = d.zsz[1]; }
+}
+
+// the user's dense pencil (x fastest) seen with the stage's (a,b) convention
+PieceMap fft_user_map(const Decomp &d, int pencil, void *ptr)
+{
+   PieceMap m{};
+   m.np = 1;
+   const int *sz = pencil == 0 ? d.xsz : pencil == 1 ? d.ysz : d.zsz;
+   const long long n1 = sz[0], n12 = (long long)sz[0] * sz[1];
+   m.e0[0] = 0;
+   m.e0[1] = sz[pencil];
+   m.ptr[0] = ptr;
+   if (pencil == 0) { m.se[0] = 1; m.sa[0] = n1; m.sb[0] = n12; }       // a = y, b = z
+   else if (pencil == 1) { m.se[0] = n1; m.sa[0] = n12; m.sb[0] = 1; } // a = z, b = x
+   else { m.se[0] = n12; m.sa[0] = 1; m.sb[0] = n1; }                   // a = x, b = y
+   return m;
+}
+
+// map of the stage on `pencil` for the link towards pencil `other`: the block exchanged with peer m
+// sits at disp[m] (reference displacement) of `peers_buf`; the block this rank keeps for itself is
+// read / written in `self_buf` (it never travels).
+PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer)
+{
+   const Side s = side_of(d, pencil, other);
+   const int me = (pencil == 0 || other == 0) ? d.c1 : d.c2;
+   // a consumer finds its own block where the producer stage (on pencil `other`) left it
+   const int64_t self_disp = consumer ? side_of(d, other, pencil).disp[me] : s.disp[me];
+   PieceMap m{};
+   m.np = s.np;
+   for (int p = 0; p < s.np; p++) {
+      m.e0[p] = s.off[p];
+      m.ptr[p] = p == me ? (char *)self_buf + (size_t)es * self_disp : (char *)peers_buf + (size_t)es * s.disp[p];
+      const long long ext = s.dist[p]; // extent of this piece along the stage's own axis
+      if (pencil == 2) {               // Z stage, Z<->Y link, block (z: ext, y: zsz1, x: zsz0)
+         m.se[p] = 1; m.sa[p] = ext * d.zsz[1]; m.sb[p] = ext;
+      } else if (pencil == 1 && other == 2) { // Y stage, Z<->Y link, block (z: ysz2, y: ext, x: ysz0)
+         m.se[p] = d.ysz[2]; m.sa[p] = 1; m.sb[p] = (long long)d.ysz[2] * ext;
+      } else if (pencil == 1) {               // Y stage, Y<->X link, block (y: ext, x: ysz0, z: ysz2)
+         m.se[p] = 1; m.sa[p] = ext * d.ysz[0]; m.sb[p] = ext;
+      } else {                                // X stage, Y<->X link, block (y: xsz1, x: ext, z: xsz2)
+         m.se[p] = d.xsz[1]; m.sa[p] = 1; m.sb[p] = (long long)d.xsz[1] * ext;
+      }
+   }
+   m.e0[s.np] = s.off[s.np];
+   return m;
+}
+
 // all-to-all(v) with the peers of the row / column communicator (self excluded).
 // Replaces decomp_2d_nccl_alltoall_{col,row}_* (src/decomp_2d_nccl.f90:214-473) / MPI_ALLTOALLV.
 void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es)

@@ -40,18 +40,29 @@ template <int TX, int LY, int MODE, bool PAIRVEC> struct Inst {
    static cudaError_t launch(const FftArgs &g, cudaStream_t st)
    {
       auto kern = fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB>;
-      static bool attr_done = false; // per-process; every device of this process runs the same binary
+      // per-process caches; every device of this process is the same part running the same binary
+      static bool attr_done = false;
+      static int resident = 0; // blocks that fit on the whole GPU at once (persistent grid)
       const size_t smem = G::needs_smem ? G::smem_bytes : 0;
-      if (!attr_done && smem > 48 * 1024) {
-         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (!attr_done) {
+         if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+         }
+         int dev = 0, sms = 0, per_sm = 0;
+         cudaError_t e = cudaGetDevice(&dev);
+         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
          if (e != cudaSuccess) return e;
+         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+         resident = sms * per_sm;
+         attr_done = true;
       }
-      attr_done = true;
       const long long tiles = (long long)((g.na + TX - 1) / TX) * g.nb;
-      const long long blocks = (tiles + LY - 1) / LY;
-      if (blocks <= 0) return cudaSuccess;
-      if (blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
-      kern<<<(unsigned)blocks, G::threads, smem, st>>>(g);
+      const long long groups = (tiles + LY - 1) / LY;
+      if (groups <= 0) return cudaSuccess;
+      const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
+      kern<<<blocks, G::threads, smem, st>>>(g);
       return cudaGetLastError();
    }
    static void reg(int kind)

@@ -295,21 +295,29 @@ template <typename T, class P, int PASS, int TX, int PADK> struct PassOp {
    }
 };
 
-template <typename T, class P, int PASS, int TX, int PADK> struct RunPasses {
+struct NoHook {
+   __device__ __forceinline__ void operator()() const {}
+};
+
+// All passes.  SYNC0: a barrier is needed before the first scatter too (the exchange buffer was used
+// as the landing zone of this tile's input).  `hook` runs right after the LAST read of the exchange
+// buffer: the buffer is free from there on (the pipelined kernel starts the next tile's loads there).
+template <typename T, class P, int PASS, int TX, int PADK, bool SYNC0, class Hook> struct RunPasses {
    using T2 = typename Vec2<T>::type;
    using PI = PlanInfo<P>;
-   static __device__ __forceinline__ void run(T2 *v, int j, T2 *lsm, const T2 *__restrict__ tw)
+   static __device__ __forceinline__ void run(T2 *v, int j, T2 *lsm, const T2 *__restrict__ tw, Hook &hook)
    {
       using Op = PassOp<T, P, PASS, TX, PADK>;
       Op::twiddle(v, j, tw);
       Op::butterflies(v);
       if constexpr (PASS + 1 < PI::npass) {
-         if (PASS > 0) __syncthreads(); // WAR: everyone has read the previous exchange
+         if (PASS > 0 || SYNC0) __syncthreads(); // WAR: everyone has read the previous contents
          Op::scatter(v, j, lsm);
          __syncthreads();
 #pragma unroll
          for (int s = 0; s < P::E; s++) v[s] = lsm[padix<PADK>(j + P::T * s) * TX];
-         RunPasses<T, P, PASS + 1, TX, PADK>::run(v, j, lsm, tw);
+         if constexpr (PASS + 2 == PI::npass) hook();
+         RunPasses<T, P, PASS + 1, TX, PADK, SYNC0, Hook>::run(v, j, lsm, tw, hook);
       } else {
          T2 w[P::E];
          Op::unpermute(v, w);
@@ -327,14 +335,39 @@ template <typename T, class P, int TX, int LY, int PADK> struct KernelGeom {
    static constexpr bool needs_smem = (PlanInfo<P>::npass > 1);
 };
 
+// ---- cp.async (LDGSTS) helpers: global -> shared without a register round trip -------------------
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem)
+{
+   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+   if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+   else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// conditional conjugation without touching the FP64 pipe: flip the sign bit of the imaginary part
+__device__ __forceinline__ double flip_sign(double y, unsigned mask_hi)
+{
+   return __hiloint2double(__double2hiint(y) ^ (int)mask_hi, __double2loint(y));
+}
+__device__ __forceinline__ float flip_sign(float y, unsigned mask_hi) { return __int_as_float(__float_as_int(y) ^ (int)mask_hi); }
+
 // The kernel.  MODE: C2C / R2C / C2R.  PAIRVEC: real pairs (2a,2a+1) are adjacent and 2*sizeof(T)
 // aligned in memory (rsa == 1, even row pitch): load/store them as one vector.
+//
+// Persistent blocks (grid = resident blocks) walk over the tile groups.  When the transform needs
+// shared memory (more than one pass) and the input is read through plain element loads (C2C, R2C),
+// the kernel is software-pipelined: the input of tile i+1 is brought in with cp.async into the very
+// buffer tile i used for its exchanges, as soon as tile i has read it for the last time, and lands
+// while tile i runs its last pass and its stores.
 template <typename T, class P, int TX, int LY, int PADK, int MODE, bool PAIRVEC, int MINB>
 __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_constant__ FftArgs g)
 {
    using T2 = typename Vec2<T>::type;
    using G = KernelGeom<T, P, TX, LY, PADK>;
    constexpr int N = P::N, E = P::E, TPL = P::T;
+   constexpr bool PIPE = G::needs_smem && MODE != MODE_C2R;
    extern __shared__ __align__(16) unsigned char smem_raw[];
    T2 *sm = reinterpret_cast<T2 *>(smem_raw);
 
@@ -342,116 +375,219 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
    const int tx = tid % TX;
    const int j = (tid / TX) % TPL;
    const int ly = tid / (TX * TPL);
-   const long long tile = (long long)blockIdx.x * LY + ly;
    const int tiles_a = (g.na + TX - 1) / TX;
-   const long long b = tile / tiles_a;
-   const long long a = (tile % tiles_a) * TX + tx;
-   const bool valid = (b < g.nb) && (a < g.na);
+   const long long ntiles = (long long)tiles_a * g.nb;
+   const long long ngroups = (ntiles + LY - 1) / LY;
    T2 *lsm = sm + (size_t)ly * (G::line_sm * TX) + tx;
    const T2 *__restrict__ tw = reinterpret_cast<const T2 *>(g.tw);
+   const unsigned conj_mask = g.backward ? 0x80000000u : 0u;
 
-   T2 v[E];
+   long long a = 0, b = 0;
+   bool valid = false, v1 = false;
+   auto locate = [&](long long grp) {
+      const long long tile = grp * LY + ly;
+      valid = tile < ntiles;
+      b = tile / tiles_a;
+      a = (tile - b * tiles_a) * TX + tx;
+      valid = valid && (a < g.na);
+      v1 = valid && (2 * a + 1 < g.na_real);
+   };
 
-   // ------------------------------------------------------------------ load
-   if constexpr (MODE == MODE_C2C) {
+   // start the asynchronous loads of the current (a,b) line into its shared-memory slots
+   auto stage = [&]() {
+      if constexpr (PIPE) {
+         if (valid) {
+            if constexpr (MODE == MODE_C2C) {
+               if (g.in.np == 1) {
+                  const T2 *p = reinterpret_cast<const T2 *>(g.in.ptr[0]) + (long long)j * g.in.se[0] + a * g.in.sa[0] + b * g.in.sb[0];
+                  const long long step = (long long)TPL * g.in.se[0];
 #pragma unroll
-      for (int s = 0; s < E; s++) {
-         T2 x = T2{0, 0};
-         if (valid) x = load_piece<T2>(g.in, j + TPL * s, a, b);
-         if (g.backward) x.y = -x.y;
-         v[s] = x;
-      }
-   } else if constexpr (MODE == MODE_R2C) {
-      const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
-      const bool v1 = valid && (2 * a + 1 < g.na_real);
+                  for (int s = 0; s < E; s++) cp_async<sizeof(T2)>(&lsm[padix<PADK>(j + TPL * s) * TX], p + s * step);
+               } else {
 #pragma unroll
-      for (int s = 0; s < E; s++) {
-         const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
-         T2 x = T2{0, 0};
-         if constexpr (PAIRVEC) {
-            if (valid) x = *reinterpret_cast<const T2 *>(rp + off);
-         } else {
-            if (valid) x.x = rp[off];
-            if (v1) x.y = rp[off + g.rsa];
-         }
-         v[s] = x;
-      }
-   } else { // C2R: build conj(Z), Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]), in shared memory
-      const bool v1 = valid && (2 * a + 1 < g.na_real);
+                  for (int s = 0; s < E; s++) {
+                     int pc;
+                     const long long off = piece_addr(g.in, j + TPL * s, a, b, pc);
+                     cp_async<sizeof(T2)>(&lsm[padix<PADK>(j + TPL * s) * TX], reinterpret_cast<const T2 *>(g.in.ptr[pc]) + off);
+                  }
+               }
+            } else { // R2C: two real lines -> (re, im) of one complex line
+               const T *p = reinterpret_cast<const T *>(g.rptr) + (long long)j * g.rse + (2 * a) * g.rsa + b * g.rsb;
+               const long long step = (long long)TPL * g.rse;
 #pragma unroll
-      for (int s = 0; s <= E / 2; s++) {
-         const int k = j + TPL * s;
-         if (k <= N / 2 && (s < E / 2 || j == 0)) {
-            T2 A = T2{0, 0}, B = T2{0, 0};
-            if (valid) A = load_piece<T2>(g.in, k, 2 * a, b);
-            if (v1) B = load_piece<T2>(g.in, k, 2 * a + 1, b);
-            if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
-            if constexpr (G::needs_smem) {
-               lsm[padix<PADK>(k) * TX] = T2{A.x - B.y, -(A.y + B.x)};
-               if (k > 0 && 2 * k < N) lsm[padix<PADK>(N - k) * TX] = T2{A.x + B.y, A.y - B.x};
-            } else { // single-thread line (T == 1, j == 0, k == s): slots are the positions
-               v[s] = T2{A.x - B.y, -(A.y + B.x)};
-               if (s > 0 && 2 * s < N) v[(N - s) % E] = T2{A.x + B.y, A.y - B.x};
+               for (int s = 0; s < E; s++) {
+                  T2 *dst = &lsm[padix<PADK>(j + TPL * s) * TX];
+                  if constexpr (PAIRVEC) cp_async<sizeof(T2)>(dst, p + s * step);
+                  else {
+                     cp_async<sizeof(T)>(&dst->x, p + s * step);
+                     if (v1) cp_async<sizeof(T)>(&dst->y, p + s * step + g.rsa);
+                  }
+               }
             }
          }
+         cp_async_commit();
       }
-      if constexpr (G::needs_smem) {
-         __syncthreads();
-#pragma unroll
-         for (int s = 0; s < E; s++) v[s] = lsm[padix<PADK>(j + TPL * s) * TX];
-         __syncthreads();
-      }
+   };
+
+   long long grp = blockIdx.x;
+   if (grp < ngroups) {
+      locate(grp);
+      stage();
    }
+   for (; grp < ngroups; grp += gridDim.x) {
+      T2 v[E];
+      const long long a_cur = a, b_cur = b;
+      const bool valid_cur = valid, v1_cur = v1;
 
-   // ------------------------------------------------------------------ transform
-   if (!g.passthrough) RunPasses<T, P, 0, TX, PADK>::run(v, j, lsm, tw);
-
-   // ------------------------------------------------------------------ store
-   if constexpr (MODE == MODE_C2C) {
+      // ------------------------------------------------------------------ load
+      if constexpr (PIPE) {
+         cp_async_wait_all(); // every thread reads back only what it staged itself: no barrier needed
 #pragma unroll
-      for (int s = 0; s < E; s++) {
-         T2 x = v[s];
-         if (g.backward) x.y = -x.y;
-         if (valid) store_piece<T2>(g.out, j + TPL * s, a, b, x);
-      }
-   } else if constexpr (MODE == MODE_C2R) {
-      T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
-      const bool v1 = valid && (2 * a + 1 < g.na_real);
-#pragma unroll
-      for (int s = 0; s < E; s++) {
-         const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
-         if constexpr (PAIRVEC) {
-            if (valid) *reinterpret_cast<T2 *>(rp + off) = T2{v[s].x, -v[s].y};
-         } else {
-            if (valid) rp[off] = v[s].x;
-            if (v1) rp[off + g.rsa] = -v[s].y;
+         for (int s = 0; s < E; s++) {
+            T2 x = lsm[padix<PADK>(j + TPL * s) * TX];
+            if constexpr (MODE == MODE_C2C) x.y = flip_sign(x.y, conj_mask);
+            else if (!v1_cur) x.y = 0;
+            v[s] = x;
          }
-      }
-   } else { // R2C: separate the two spectra.  A[k] = (Z[k] + conj Z[n-k])/2, B[k] = (Z[k] - conj Z[n-k])/(2i)
-      const bool v1 = valid && (2 * a + 1 < g.na_real);
-      if constexpr (G::needs_smem) {
-         __syncthreads();
+      } else if constexpr (MODE == MODE_C2C) {
 #pragma unroll
-         for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * TX] = v[s];
-         __syncthreads();
-      }
+         for (int s = 0; s < E; s++) {
+            T2 x = T2{0, 0};
+            if (valid_cur) x = load_piece<T2>(g.in, j + TPL * s, a_cur, b_cur);
+            x.y = flip_sign(x.y, conj_mask);
+            v[s] = x;
+         }
+      } else if constexpr (MODE == MODE_R2C) {
+         const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
 #pragma unroll
-      for (int s = 0; s <= E / 2; s++) {
-         const int k = j + TPL * s;
-         if (k <= N / 2 && (s < E / 2 || j == 0)) {
-            T2 zk, zn;
-            zk = v[s]; // slot s holds Z[j + T s] = Z[k]
-            if constexpr (G::needs_smem) {
-               zn = lsm[padix<PADK>((N - k) % N) * TX];
-            } else { // T == 1: k == s
-               zn = v[(N - s) % N];
+         for (int s = 0; s < E; s++) {
+            const long long off = (long long)(j + TPL * s) * g.rse + (2 * a_cur) * g.rsa + b_cur * g.rsb;
+            T2 x = T2{0, 0};
+            if constexpr (PAIRVEC) {
+               if (valid_cur) x = *reinterpret_cast<const T2 *>(rp + off);
+            } else {
+               if (valid_cur) x.x = rp[off];
+               if (v1_cur) x.y = rp[off + g.rsa];
             }
-            const T hf = (T)0.5;
-            T2 A = T2{(zk.x + zn.x) * hf, (zk.y - zn.y) * hf};
-            T2 B = T2{(zk.y + zn.y) * hf, (zn.x - zk.x) * hf};
-            if (valid) store_piece<T2>(g.out, k, 2 * a, b, A);
-            if (v1) store_piece<T2>(g.out, k, 2 * a + 1, b, B);
+            v[s] = x;
          }
+      } else { // C2R: build conj(Z), Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k])
+#pragma unroll
+         for (int s = 0; s <= E / 2; s++) {
+            const int k = j + TPL * s;
+            if (k <= N / 2 && (s < E / 2 || j == 0)) {
+               T2 A = T2{0, 0}, B = T2{0, 0};
+               if (valid_cur) A = load_piece<T2>(g.in, k, 2 * a_cur, b_cur);
+               if (v1_cur) B = load_piece<T2>(g.in, k, 2 * a_cur + 1, b_cur);
+               if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
+               if constexpr (G::needs_smem) {
+                  lsm[padix<PADK>(k) * TX] = T2{A.x - B.y, -(A.y + B.x)};
+                  if (k > 0 && 2 * k < N) lsm[padix<PADK>(N - k) * TX] = T2{A.x + B.y, A.y - B.x};
+               } else { // single-thread line (T == 1, j == 0, k == s): slots are the positions
+                  v[s] = T2{A.x - B.y, -(A.y + B.x)};
+                  if (s > 0 && 2 * s < N) v[(N - s) % E] = T2{A.x + B.y, A.y - B.x};
+               }
+            }
+         }
+         if constexpr (G::needs_smem) {
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < E; s++) v[s] = lsm[padix<PADK>(j + TPL * s) * TX];
+            __syncthreads();
+         }
+      }
+
+      // next tile of this block
+      const long long nxt = grp + gridDim.x;
+      auto prefetch_next = [&]() {
+         if constexpr (PIPE) {
+            __syncthreads(); // the whole block is done with the exchange buffer
+            if (nxt < ngroups) {
+               locate(nxt);
+               stage();
+            }
+         }
+      };
+
+      // ------------------------------------------------------------------ transform
+      if (!g.passthrough) {
+         if constexpr (PIPE && MODE == MODE_C2C) {
+            RunPasses<T, P, 0, TX, PADK, true, decltype(prefetch_next)>::run(v, j, lsm, tw, prefetch_next);
+         } else {
+            NoHook nh;
+            RunPasses<T, P, 0, TX, PADK, PIPE, NoHook>::run(v, j, lsm, tw, nh);
+         }
+      } else if constexpr (PIPE && MODE == MODE_C2C) {
+         prefetch_next();
+      }
+
+      // ------------------------------------------------------------------ store
+      if constexpr (MODE == MODE_C2C) {
+         if (valid_cur) {
+            if (g.out.np == 1) {
+               T2 *p = reinterpret_cast<T2 *>(g.out.ptr[0]) + (long long)j * g.out.se[0] + a_cur * g.out.sa[0] + b_cur * g.out.sb[0];
+               const long long step = (long long)TPL * g.out.se[0];
+#pragma unroll
+               for (int s = 0; s < E; s++) {
+                  T2 x = v[s];
+                  x.y = flip_sign(x.y, conj_mask);
+                  p[s * step] = x;
+               }
+            } else {
+#pragma unroll
+               for (int s = 0; s < E; s++) {
+                  T2 x = v[s];
+                  x.y = flip_sign(x.y, conj_mask);
+                  store_piece<T2>(g.out, j + TPL * s, a_cur, b_cur, x);
+               }
+            }
+         }
+      } else if constexpr (MODE == MODE_C2R) {
+         T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
+#pragma unroll
+         for (int s = 0; s < E; s++) {
+            const long long off = (long long)(j + TPL * s) * g.rse + (2 * a_cur) * g.rsa + b_cur * g.rsb;
+            if constexpr (PAIRVEC) {
+               if (valid_cur) *reinterpret_cast<T2 *>(rp + off) = T2{v[s].x, -v[s].y};
+            } else {
+               if (valid_cur) rp[off] = v[s].x;
+               if (v1_cur) rp[off + g.rsa] = -v[s].y;
+            }
+         }
+         if constexpr (G::needs_smem) __syncthreads(); // next iteration's prologue overwrites the buffer
+      } else { // R2C: separate the two spectra.  A[k] = (Z[k] + conj Z[n-k])/2, B[k] = (Z[k] - conj Z[n-k])/(2i)
+         if constexpr (G::needs_smem) {
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * TX] = v[s];
+            __syncthreads();
+         }
+         T2 zn[E / 2 + 1];
+#pragma unroll
+         for (int s = 0; s <= E / 2; s++) {
+            const int k = j + TPL * s;
+            zn[s] = T2{0, 0};
+            if (k <= N / 2 && (s < E / 2 || j == 0)) {
+               if constexpr (G::needs_smem) zn[s] = lsm[padix<PADK>((N - k) % N) * TX];
+               else zn[s] = v[(N - s) % N]; // T == 1: k == s
+            }
+         }
+         prefetch_next(); // (no-op unless pipelined) the exchange buffer is free again
+#pragma unroll
+         for (int s = 0; s <= E / 2; s++) {
+            const int k = j + TPL * s;
+            if (k <= N / 2 && (s < E / 2 || j == 0)) {
+               const T2 zk = v[s]; // slot s holds Z[j + T s] = Z[k]
+               const T hf = (T)0.5;
+               T2 A = T2{(zk.x + zn[s].x) * hf, (zk.y - zn[s].y) * hf};
+               T2 B = T2{(zk.y + zn[s].y) * hf, (zn[s].x - zk.x) * hf};
+               if (valid_cur) store_piece<T2>(g.out, k, 2 * a_cur, b_cur, A);
+               if (v1_cur) store_piece<T2>(g.out, k, 2 * a_cur + 1, b_cur, B);
+            }
+         }
+      }
+      if constexpr (!PIPE) {
+         if (nxt < ngroups) locate(nxt);
       }
    }
 }

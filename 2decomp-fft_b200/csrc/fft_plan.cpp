@@ -27,9 +27,11 @@ static const int *pencil_size(const Decomp &d, int p) { return p == 0 ? d.xsz : 
 
 // One batched 1-D stage along `pencil` of the complex-side decomp dc (real side: dr, R2C/C2R only).
 // This is c2c_1m_{x,y,z} / r2c_1m_{x,z} / c2r_1m_{x,z} (src/fft_cufft.f90:489-671) fused with the
-// neighbouring mem_split_* / mem_merge_* through the maps.
+// neighbouring mem_split_* / mem_merge_* through the maps.  `chain`: the stage is part of a 3-D
+// transform and uses the (a,b) batch convention of the private wire layouts (decomp.cpp); otherwise
+// it works on one dense local array.
 static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc, const Decomp *dr, const PieceMap &in,
-                      const PieceMap &out, void *rptr, int backward, int passthrough)
+                      const PieceMap &out, void *rptr, int backward, int passthrough, bool chain)
 {
    const int *cs = pencil_size(dc, pencil);
    FftArgs g{};
@@ -37,11 +39,14 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    g.out = out;
    g.backward = backward;
    g.passthrough = passthrough;
-   int lines;
-   if (pencil == 0) { g.na = cs[1] * cs[2]; g.nb = 1; }
-   else if (pencil == 1) { g.na = cs[0]; g.nb = cs[2]; }
-   else { g.na = cs[0] * cs[1]; g.nb = 1; }
-   lines = g.na * g.nb;
+   int kind;
+   if (chain) {
+      fft_stage_batch(dc, pencil, g.na, g.nb);
+      kind = KIND_TILE;
+   } else if (pencil == 0) { g.na = cs[1] * cs[2]; g.nb = 1; kind = KIND_LINE; }
+   else if (pencil == 1) { g.na = cs[0]; g.nb = cs[2]; kind = KIND_TILE; }
+   else { g.na = cs[0] * cs[1]; g.nb = 1; kind = KIND_TILE; }
+   const long long lines = (long long)g.na * g.nb;
    int n = cs[pencil];
    int pairvec = 0;
    const int rs = f64 ? 8 : 4;
@@ -54,16 +59,19 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
       g.rptr = rptr;
       g.na_real = g.na;
       g.na = (g.na_real + 1) / 2;
-      if (pencil == 0) { g.rse = 1; g.rsa = n; g.rsb = 0; }
-      else {
-         g.rse = (long long)rsz[0] * rsz[1]; g.rsa = 1; g.rsb = 0;
-         pairvec = ((g.rse % 2) == 0 && ((uintptr_t)rptr % (2 * rs)) == 0) ? 1 : 0;
+      const long long r1 = rsz[0], r12 = (long long)rsz[0] * rsz[1];
+      if (pencil == 0) { // lines along x; chain: a = y, b = z; dense: a = (y,z) flattened
+         g.rse = 1; g.rsa = r1; g.rsb = chain ? r12 : 0;
+      } else { // lines along z; chain: a = x, b = y; dense: a = (x,y) flattened
+         g.rse = r12; g.rsa = 1; g.rsb = chain ? r1 : 0;
+         // pairs (a, a+1) are adjacent reals: one vector access when every pair is 2*sizeof(T) aligned
+         const bool even_rows = chain ? (r1 % 2 == 0) : (r12 % 2 == 0);
+         pairvec = (even_rows && ((uintptr_t)rptr % (2 * rs)) == 0) ? 1 : 0;
       }
       bytes = (double)lines * n * rs + (double)lines * (n / 2 + 1) * 2 * rs;
    }
    g.n = n;
    if (lines == 0) return;
-   const int kind = pencil == 0 ? KIND_LINE : KIND_TILE;
    const FftKernelInfo *k = fft_find(n, f64, kind, mode, pairvec);
    D2D_REQUIRE(k != nullptr, "transform length " + std::to_string(n) + " is not supported by the compiled kernels");
    g.tw = twiddles_for(ctx->device, n, f64);
@@ -80,76 +88,57 @@ struct StageDef {
    int pencil, mode;
 };
 
-// Generic 3-stage chain.  `in`/`out` are the user arrays; exactly one of them is real for r2c/c2r.
-static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward,
-                      bool in_writable)
+// Generic 3-stage chain.  `in`/`out` are the user arrays (dense pencils); exactly one of them is real
+// for r2c/c2r.  Between two stages the data lives in a work buffer in the private wire layout of
+// that link (decomp.cpp): the producer writes its send blocks (the block it keeps for itself
+// included), the exchange moves the other blocks into a second buffer, the consumer gathers from
+// both.  With a 1-rank communicator the exchange vanishes and the consumer reads the producer's
+// buffer.  Three work buffers rotate; a single-rank complex-output transform borrows `out` as the
+// first one.
+static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
    Ctx *ctx = p.ctx;
    const int es = p.f64 ? 16 : 8;
-   const bool final_complex = st[2].mode == MODE_C2C;
    const size_t wbytes = (size_t)es * dc.max_pencil();
-   bool live[3] = {false, false, false}; // work buffers holding the current stage's input
-   auto pick = [&](int avoid) {
+   const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C;
+   int live_a = -1, live_b = -1; // work buffers holding the current stage's input
+   auto pick = [&]() {
       for (int i = 0; i < 3; i++)
-         if (!live[i] && i != avoid) return i;
-      D2D_REQUIRE(false, "internal: no free work buffer");
+         if (i != live_a && i != live_b) return i;
       return -1;
    };
-   PieceMap cur = natural_map(dc, st[0].pencil, in); // complex input map (unused for R2C)
-   void *cur_nat = (st[0].mode == MODE_C2C && in_writable) ? in : nullptr; // natural complex buffer we may overwrite
-   int cur_w = -1;                                                             // ... and its work-buffer index, if any
+   PieceMap cur = fft_user_map(dc, st[0].pencil, in); // complex input map (unused for R2C)
    for (int s = 0; s < 3; s++) {
       const int pen = st[s].pencil, mode = st[s].mode;
       const bool last = (s == 2);
-      const bool exch = !last && comm_size(dc, pen, st[s + 1].pencil) > 1;
-      bool later_local = true;
-      for (int t = s; t < 2; t++) later_local = later_local && comm_size(dc, st[t].pencil, st[t + 1].pencil) == 1;
       const int passthrough = (mode == MODE_C2C && p.skip[pen]) ? 1 : 0;
       PieceMap om{};
-      void *rptr = nullptr;
-      void *dst_nat = nullptr;
-      int dst_w = -1, send_w = -1;
+      void *rptr = nullptr, *sendbuf = nullptr;
+      int send_w = -1;
       if (mode == MODE_R2C) rptr = in;
       if (last) {
          if (mode == MODE_C2R) rptr = out;
-         else { om = natural_map(dc, pen, out); dst_nat = out; }
-      } else if (exch) {
-         send_w = pick(-1);
-         om = send_map(dc, pen, st[s + 1].pencil, ctx->reserve(send_w, wbytes), es);
+         else om = fft_user_map(dc, pen, out);
       } else {
-         if (mode == MODE_C2C && cur_nat) { dst_nat = cur_nat; dst_w = cur_w; } // in place
-         else if (final_complex && later_local) dst_nat = out;
-         else { dst_w = pick(-1); dst_nat = ctx->reserve(dst_w, wbytes); }
-         om = natural_map(dc, pen, dst_nat);
+         if (s == 0 && borrow_out) sendbuf = out;
+         else { send_w = pick(); sendbuf = ctx->reserve(send_w, wbytes); }
+         om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false);
       }
-      const bool noop = passthrough && !exch && dst_nat && dst_nat == cur_nat;
-      if (!noop) run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough);
+      run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
       if (last) break;
       const int nxt = st[s + 1].pencil;
-      if (exch) {
-         // the input buffers of this stage are free once it has run (stream order)
-         bool was[3] = {live[0], live[1], live[2]};
-         live[0] = live[1] = live[2] = false;
-         live[send_w] = true;
-         int recv_w = -1;
-         for (int i = 0; i < 3; i++)
-            if (was[i] && i != send_w) { recv_w = i; break; }
-         if (recv_w < 0) recv_w = pick(-1);
-         void *sb = ctx->work[send_w];
-         void *rb = ctx->reserve(recv_w, wbytes);
-         sb = ctx->work[send_w];
-         exchange(ctx, dc, pen, nxt, sb, rb, es);
-         live[recv_w] = true;
-         cur = recv_map(dc, pen, nxt, rb, sb, es);
-         cur_nat = nullptr;
-         cur_w = -1;
-      } else {
-         live[0] = live[1] = live[2] = false;
-         if (dst_w >= 0) live[dst_w] = true;
-         cur = natural_map(dc, nxt, dst_nat);
-         cur_nat = dst_nat;
-         cur_w = dst_w;
+      // the input buffers of this stage are free once it has run (stream order)
+      const int old_a = live_a, old_b = live_b;
+      live_a = send_w;
+      live_b = -1;
+      void *recvbuf = nullptr;
+      if (comm_size(dc, pen, nxt) > 1) {
+         int recv_w = (old_a >= 0 && old_a != send_w) ? old_a : (old_b >= 0 && old_b != send_w) ? old_b : pick();
+         recvbuf = ctx->reserve(recv_w, wbytes);
+         live_b = recv_w;
+         exchange(ctx, dc, pen, nxt, sendbuf, recvbuf, es);
       }
+      cur = fft_link_map(dc, nxt, pen, recvbuf, sendbuf, es, true);
    }
 }
 
@@ -160,7 +149,8 @@ static void reserve_all(Plan &p)
    const size_t wb = (size_t)es * std::max(p.sp.d.max_pencil(), p.ph.d.max_pencil());
    const bool multi = p.ctx->nranks > 1;
    p.ctx->reserve(0, wb);
-   if (multi) { p.ctx->reserve(1, wb); p.ctx->reserve(2, wb); }
+   p.ctx->reserve(1, wb);
+   if (multi) p.ctx->reserve(2, wb);
 }
 
 Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])
@@ -205,7 +195,7 @@ void fft_3d_c2c(Plan *p, void *in, void *out, int isign)
                     (p->format == D2D_PHYSICAL_IN_Z && isign == D2D_FFT_BACKWARD);
    const StageDef a[3] = {{0, MODE_C2C}, {1, MODE_C2C}, {2, MODE_C2C}};
    const StageDef b[3] = {{2, MODE_C2C}, {1, MODE_C2C}, {0, MODE_C2C}};
-   run_chain(*p, p->ph.d, nullptr, xyz ? a : b, in, out, isign == D2D_FFT_BACKWARD, p->inplace != 0);
+   run_chain(*p, p->ph.d, nullptr, xyz ? a : b, in, out, isign == D2D_FFT_BACKWARD);
 }
 
 // fft_3d_r2c (src/fft_cufft.f90:795-934)
@@ -215,7 +205,7 @@ void fft_3d_r2c(Plan *p, const void *in_r, void *out_c)
    ProfScope ps(p->ctx, "fft_r2c");
    const StageDef x[3] = {{0, MODE_R2C}, {1, MODE_C2C}, {2, MODE_C2C}};
    const StageDef z[3] = {{2, MODE_R2C}, {1, MODE_C2C}, {0, MODE_C2C}};
-   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, const_cast<void *>(in_r), out_c, 0, false);
+   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, const_cast<void *>(in_r), out_c, 0);
 }
 
 // fft_3d_c2r (src/fft_cufft.f90:939-1170)
@@ -225,7 +215,7 @@ void fft_3d_c2r(Plan *p, void *in_c, void *out_r)
    ProfScope ps(p->ctx, "fft_c2r");
    const StageDef x[3] = {{2, MODE_C2C}, {1, MODE_C2C}, {0, MODE_C2R}};
    const StageDef z[3] = {{0, MODE_C2C}, {1, MODE_C2C}, {2, MODE_C2R}};
-   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, in_c, out_r, 1, p->inplace != 0);
+   run_chain(*p, p->sp.d, &p->ph.d, p->format == D2D_PHYSICAL_IN_X ? x : z, in_c, out_r, 1);
 }
 
 // sizes (bytes) of the user arrays of a plan: [0] real physical, [1] complex spectral, [2] complex physical (c2c in), [3] complex c2c out
@@ -320,16 +310,16 @@ void fft_1m(Ctx *ctx, int dtype, int mode, int axis, int n1, int n2, int n3, con
    decomp_init(dr, n1, n2, n3, 1, 1, 0);
    if (mode == MODE_C2C) {
       run_stage(ctx, f64, mode, axis, dr, nullptr, natural_map(dr, axis, const_cast<void *>(in)), natural_map(dr, axis, out), nullptr,
-                isign == D2D_FFT_BACKWARD, 0);
+                isign == D2D_FFT_BACKWARD, 0, false);
       return;
    }
    D2D_REQUIRE(axis == 0 || axis == 2, "real transforms run along x or z only");
    const int c1 = axis == 0 ? n1 / 2 + 1 : n1, c3 = axis == 2 ? n3 / 2 + 1 : n3;
    decomp_init(dc, c1, n2, c3, 1, 1, 0);
    if (mode == MODE_R2C)
-      run_stage(ctx, f64, mode, axis, dc, &dr, PieceMap{}, natural_map(dc, axis, out), const_cast<void *>(in), 0, 0);
+      run_stage(ctx, f64, mode, axis, dc, &dr, PieceMap{}, natural_map(dc, axis, out), const_cast<void *>(in), 0, 0, false);
    else
-      run_stage(ctx, f64, mode, axis, dc, &dr, natural_map(dc, axis, const_cast<void *>(in)), PieceMap{}, out, 1, 0);
+      run_stage(ctx, f64, mode, axis, dc, &dr, natural_map(dc, axis, const_cast<void *>(in)), PieceMap{}, out, 1, 0, false);
 }
 
 } // namespace d2d

@@ -138,6 +138,16 @@ const char *d2d_version(void);
 /* number of compiled FFT kernel instantiations, and a description of entry i (diagnostics) */
 int d2d_fft_kernel_count(void);
 int d2d_fft_kernel_describe(int i, char *buf, int buflen);
+/* Host-only view of the private wire layout used inside decomp_2d_fft_3d (diagnostics / CPU tests):
+ * the piece map of the stage on `pencil` (0 x, 1 y, 2 z) for the link towards pencil `other`, as a
+ * producer (consumer = 0) or consumer (1).  Element e of line (a,b) lives at element offset
+ * off[m] + (e - e0[m]) se[m] + a sa[m] + b sb[m] of the peers' buffer (in_self[m] = 0: the receive
+ * buffer for a consumer, the send buffer for a producer) or of the buffer holding this rank's own
+ * block (in_self[m] = 1: always the producer's send buffer).  na/nb = batch extents of the stage. */
+int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int *np, int e0[9], int64_t off[8],
+                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb);
+/* the user's dense pencil seen with the same (a,b) convention */
+int d2d_debug_user_map(const d2d_decomp *decomp, int pencil, int64_t *se, int64_t *sa, int64_t *sb, int *n, int *na, int *nb);
 
 #ifdef __cplusplus
 }

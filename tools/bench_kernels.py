@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--prec", default="f64")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--shape", default=None, help="nx,ny,nz (default n,n,n)")
+    ap.add_argument("--only1d", action="store_true")
+    ap.add_argument("--axes", default="0,1,2")
+    ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     p = package()
     shape = tuple(int(x) for x in a.shape.split(",")) if a.shape else (a.n,) * 3
@@ -37,8 +40,8 @@ def main():
     cz = d2d.alloc_x(cdt)  # (nx,ny,nz) complex
     cz.real.normal_()
     res = {}
-    for axis in (0, 1, 2):
-        for _ in range(2):
+    for axis in [int(x) for x in a.axes.split(',')]:
+        for _ in range(a.warm):
             d2d.c2c_1m(cz, axis, -1)
         d2d.sync()
         d2d.profile_reset()
@@ -54,7 +57,7 @@ def main():
     del cz
     torch.cuda.empty_cache()
     # full 3-D pair, PHYSICAL_IN_Z (headline) and PHYSICAL_IN_X
-    for fmt, name in ((p.PHYSICAL_IN_Z, "Z"), (p.PHYSICAL_IN_X, "X")):
+    for fmt, name in (() if a.only1d else ((p.PHYSICAL_IN_Z, "Z"), (p.PHYSICAL_IN_X, "X"))):
         eng = p.decomp_2d_fft_init(fmt, dtype=rdt)
         a_in = (d2d.alloc_z if fmt == p.PHYSICAL_IN_Z else d2d.alloc_x)(rdt, eng.ph)
         a_out = (d2d.alloc_x if fmt == p.PHYSICAL_IN_Z else d2d.alloc_z)(cdt, eng.sp)
