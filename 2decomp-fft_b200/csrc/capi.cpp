@@ -412,13 +412,16 @@ int d2d_memcpy_async(d2d_ctx *ctx, void *dst, const void *src, int64_t bytes, in
 }
 
 int d2d_fft_kernel_count(void) { return fft_registry_size(); }
-int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int *np, int e0[9], int64_t off[8],
-                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb)
+int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int padq, int *np, int e0[9], int64_t off[8],
+                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb, int64_t cnt[8], int64_t disp[8])
 {
    D2D_TRY
    D2D_REQUIRE((pencil == 1 && (other == 0 || other == 2)) || (other == 1 && (pencil == 0 || pencil == 2)), "not a link");
    char *peers = reinterpret_cast<char *>(uintptr_t(1) << 44), *self = reinterpret_cast<char *>(uintptr_t(1) << 45);
-   const PieceMap m = fft_link_map(decomp->d, pencil, other, peers, self, 1, consumer != 0);
+   const PieceMap m = fft_link_map(decomp->d, pencil, other, peers, self, 1, consumer != 0, padq);
+   LinkSide L;
+   fft_link_side(decomp->d, pencil, other, padq, L);
+   for (int p = 0; p < L.np; p++) { cnt[p] = L.cnt[p]; disp[p] = L.disp[p]; }
    *np = m.np;
    for (int p = 0; p <= m.np; p++) e0[p] = m.e0[p];
    for (int p = 0; p < m.np; p++) {

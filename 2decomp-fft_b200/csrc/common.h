@@ -163,7 +163,16 @@ int comm_size(const Decomp &d, int from, int to);
 // private wire layouts of the fused 3-D transforms (decomp.cpp)
 void fft_stage_batch(const Decomp &d, int pencil, int &na, int &nb);
 PieceMap fft_user_map(const Decomp &d, int pencil, void *ptr);
-PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer);
+struct LinkSide {
+   int np, me;
+   int e0[kMaxP + 1];
+   int64_t cnt[kMaxP], disp[kMaxP], total;
+   long long se[kMaxP], sa[kMaxP], sb[kMaxP];
+};
+void fft_link_side(const Decomp &d, int pencil, int other, int padq, LinkSide &L);
+int64_t fft_work_elems(const Decomp &d, int padq);
+PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer, int padq);
+void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int padq);
 
 void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src, void *dst);
 

@@ -22,10 +22,10 @@ static std::vector<FftKernelInfo> &registry()
    return r;
 }
 void fft_register(const FftKernelInfo &k) { registry().push_back(k); }
-const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec)
+const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, int line_in)
 {
    for (const auto &k : registry())
-      if (k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec) return &k;
+      if (k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec && k.line_in == line_in) return &k;
    return nullptr;
 }
 int fft_registry_size() { return (int)registry().size(); }

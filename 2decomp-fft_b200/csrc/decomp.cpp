@@ -183,33 +183,107 @@ PieceMap fft_user_map(const Decomp &d, int pencil, void *ptr)
    return m;
 }
 
-// map of the stage on `pencil` for the link towards pencil `other`: the block exchanged with peer m
-// sits at disp[m] (reference displacement) of `peers_buf`; the block this rank keeps for itself is
-// read / written in `self_buf` (it never travels).
-PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer)
+// One side of a link, seen from this rank: the stage on `pencil` talking to the stage on `other`.
+// Blocks are padded along their unit-stride axis to a multiple of `padq` elements (128 B) so that
+// every row of every block starts on a 128-byte boundary even for ragged extents like nz/2+1 = 513
+// (measured: a 16-byte-misaligned 513-element row costs 2.2x the L2 sectors and read-modify-write
+// of partial sectors on the store side).  Counts / displacements are therefore this library's own
+// (the reference's x1cnts... stay untouched for the bare transpose API).
+void fft_link_side(const Decomp &d, int pencil, int other, int padq, LinkSide &L)
 {
    const Side s = side_of(d, pencil, other);
-   const int me = (pencil == 0 || other == 0) ? d.c1 : d.c2;
-   // a consumer finds its own block where the producer stage (on pencil `other`) left it
-   const int64_t self_disp = consumer ? side_of(d, other, pencil).disp[me] : s.disp[me];
-   PieceMap m{};
-   m.np = s.np;
+   auto pad = [&](long long v) { return (v + padq - 1) / padq * padq; };
+   L = LinkSide{};
+   L.np = s.np;
+   L.me = (pencil == 0 || other == 0) ? d.c1 : d.c2;
+   int64_t disp = 0;
    for (int p = 0; p < s.np; p++) {
-      m.e0[p] = s.off[p];
-      m.ptr[p] = p == me ? (char *)self_buf + (size_t)es * self_disp : (char *)peers_buf + (size_t)es * s.disp[p];
+      L.e0[p] = s.off[p];
       const long long ext = s.dist[p]; // extent of this piece along the stage's own axis
-      if (pencil == 2) {               // Z stage, Z<->Y link, block (z: ext, y: zsz1, x: zsz0)
-         m.se[p] = 1; m.sa[p] = ext * d.zsz[1]; m.sb[p] = ext;
-      } else if (pencil == 1 && other == 2) { // Y stage, Z<->Y link, block (z: ysz2, y: ext, x: ysz0)
-         m.se[p] = d.ysz[2]; m.sa[p] = 1; m.sb[p] = (long long)d.ysz[2] * ext;
-      } else if (pencil == 1) {               // Y stage, Y<->X link, block (y: ext, x: ysz0, z: ysz2)
-         m.se[p] = 1; m.sa[p] = ext * d.ysz[0]; m.sb[p] = ext;
-      } else {                                // X stage, Y<->X link, block (y: xsz1, x: ext, z: xsz2)
-         m.se[p] = d.xsz[1]; m.sa[p] = 1; m.sb[p] = (long long)d.xsz[1] * ext;
+      if (pencil == 2) {               // Z stage, Z<->Y link, block (z: pad(ext), y: zsz1, x: zsz0)
+         const long long wp = pad(ext);
+         L.se[p] = 1; L.sa[p] = wp * d.zsz[1]; L.sb[p] = wp;
+         L.cnt[p] = wp * d.zsz[1] * d.zsz[0];
+      } else if (pencil == 1 && other == 2) { // Y stage, Z<->Y link, block (z: pad(ysz2), y: ext, x: ysz0)
+         const long long wp = pad(d.ysz[2]);
+         L.se[p] = wp; L.sa[p] = 1; L.sb[p] = wp * ext;
+         L.cnt[p] = wp * ext * d.ysz[0];
+      } else if (pencil == 1) {               // Y stage, Y<->X link, block (y: pad(ext), x: ysz0, z: ysz2)
+         const long long hp = pad(ext);
+         L.se[p] = 1; L.sa[p] = hp * d.ysz[0]; L.sb[p] = hp;
+         L.cnt[p] = hp * d.ysz[0] * d.ysz[2];
+      } else {                                // X stage, Y<->X link, block (y: pad(xsz1), x: ext, z: xsz2)
+         const long long hp = pad(d.xsz[1]);
+         L.se[p] = hp; L.sa[p] = 1; L.sb[p] = hp * ext;
+         L.cnt[p] = hp * ext * d.xsz[2];
       }
+      L.disp[p] = disp;
+      disp += L.cnt[p];
    }
-   m.e0[s.np] = s.off[s.np];
+   L.e0[s.np] = s.off[s.np];
+   L.total = disp;
+}
+
+// largest buffer (in elements) any stage of a 3-D transform on this decomp writes or receives
+int64_t fft_work_elems(const Decomp &d, int padq)
+{
+   int64_t m = d.max_pencil();
+   static const int sides[4][2] = {{2, 1}, {1, 2}, {1, 0}, {0, 1}};
+   for (auto &sd : sides) {
+      LinkSide L;
+      fft_link_side(d, sd[0], sd[1], padq, L);
+      m = std::max(m, L.total);
+   }
    return m;
+}
+
+// map of the stage on `pencil` for the link towards `other`.  Producer: every block (its own
+// included) is written into `self_buf`.  Consumer: the peers' blocks are read from `peers_buf`
+// (the receive buffer); the block this rank kept for itself is read where its producer stage left
+// it in `self_buf` (it never travels).
+PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer, int padq)
+{
+   LinkSide L, P;
+   fft_link_side(d, pencil, other, padq, L);
+   fft_link_side(d, other, pencil, padq, P);
+   PieceMap m{};
+   m.np = L.np;
+   for (int p = 0; p < L.np; p++) {
+      m.e0[p] = L.e0[p];
+      if (!consumer) m.ptr[p] = (char *)self_buf + (size_t)es * L.disp[p];
+      else if (p == L.me) m.ptr[p] = (char *)self_buf + (size_t)es * P.disp[L.me];
+      else m.ptr[p] = (char *)peers_buf + (size_t)es * L.disp[p];
+      m.se[p] = L.se[p]; m.sa[p] = L.sa[p]; m.sb[p] = L.sb[p];
+   }
+   m.e0[L.np] = L.e0[L.np];
+   return m;
+}
+
+// the all-to-all(v) of a fused 3-D transform: producer side on pencil `from`, consumer on `to`
+void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int padq)
+{
+   LinkSide S, R;
+   fft_link_side(d, from, to, padq, S);
+   fft_link_side(d, to, from, padq, R);
+   if (S.np == 1) return;
+   D2D_REQUIRE(ctx->tr != nullptr, "context has no transport but the process grid has more than one rank");
+   const bool col = (from == 0 || to == 0);
+   std::vector<PeerXfer> xf;
+   double bytes = 0;
+   for (int k = 1; k < S.np; k++) {
+      const int m = (S.me + k) % S.np; // stagger the peers
+      PeerXfer x;
+      x.peer = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
+      x.sendptr = (const char *)sendbuf + (size_t)es * S.disp[m];
+      x.sendbytes = (size_t)es * S.cnt[m];
+      x.recvptr = (char *)recvbuf + (size_t)es * R.disp[m];
+      x.recvbytes = (size_t)es * R.cnt[m];
+      bytes += (double)x.sendbytes;
+      xf.push_back(x);
+   }
+   static const char *names[3][3] = {{"", "a2a_x_y", ""}, {"a2a_y_x", "", "a2a_y_z"}, {"", "a2a_z_y", ""}};
+   ProfScope ps(ctx, names[from][to], bytes);
+   ctx->tr->exchange(xf, ctx->stream);
 }
 
 // all-to-all(v) with the peers of the row / column communicator (self excluded).

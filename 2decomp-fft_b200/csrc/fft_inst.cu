@@ -30,16 +30,19 @@ constexpr int LY_LINE = cmax(1, cmin(kTargetThreads / P::T, kMaxSmem / kLineByte
 constexpr int TX_WANT = 64 / (int)sizeof(T2);
 constexpr int TX_TILE = cmax(1, cmin(TX_WANT, cmin(1024 / P::T, kMaxSmem / kLineBytes)));
 constexpr int LY_TILE = cmax(1, cmin(kTargetThreads / (TX_TILE * P::T), kMaxSmem / (kLineBytes * TX_TILE)));
-constexpr int PADK = 16;
+// wide tiles (128 B rows) for the stages whose far side is a user array with a huge row pitch
+constexpr int TX_WIDE = cmax(1, cmin(2 * TX_WANT, cmin(1024 / P::T, (200 * 1024) / kLineBytes)));
+constexpr int LY_WIDE = cmax(1, cmin(kTargetThreads / (TX_WIDE * P::T), kMaxSmem / (kLineBytes * TX_WIDE)));
+constexpr int PADK = P::R0; // one padding element per first-pass butterfly (bank-conflict model: tools/smem_conflicts.py)
 
 constexpr int minb_for(int threads) { return cmax(1, (D2D_F64 ? 512 : 768) / threads); }
 
-template <int TX, int LY, int MODE, bool PAIRVEC> struct Inst {
-   using G = KernelGeom<real_t, P, TX, LY, PADK>;
+template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
+   using G = KernelGeom<real_t, P, TX, LY, PADK, LM>;
    static constexpr int MINB = minb_for(G::threads);
    static cudaError_t launch(const FftArgs &g, cudaStream_t st)
    {
-      auto kern = fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB>;
+      auto kern = fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB, LM>;
       // per-process caches; every device of this process is the same part running the same binary
       static bool attr_done = false;
       static int resident = 0; // blocks that fit on the whole GPU at once (persistent grid)
@@ -74,7 +77,8 @@ template <int TX, int LY, int MODE, bool PAIRVEC> struct Inst {
       k.smem = G::needs_smem ? G::smem_bytes : 0;
       k.tw_total = PI::tw_total; k.npass = PI::npass;
       for (int p = 0; p < 4; p++) k.radix[p] = PI::radix(p);
-      k.func = (const void *)fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB>;
+      k.func = (const void *)fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB, LM>;
+      k.line_in = LM ? 1 : 0;
       k.launch = &launch;
       fft_register(k);
    }
@@ -91,6 +95,14 @@ struct Registrar {
       Inst<TX_TILE, LY_TILE, MODE_C2R, true>::reg(KIND_TILE);
       Inst<TX_TILE, LY_TILE, MODE_R2C, false>::reg(KIND_TILE);
       Inst<TX_TILE, LY_TILE, MODE_C2R, false>::reg(KIND_TILE);
+      if constexpr (TX_TILE > 1 && PlanInfo<P>::npass > 1) { // line-like inputs: line-major shared memory
+         Inst<TX_TILE, LY_TILE, MODE_C2C, false, true>::reg(KIND_TILE);
+         Inst<TX_TILE, LY_TILE, MODE_R2C, false, true>::reg(KIND_TILE);
+      }
+      if constexpr (TX_WIDE > TX_TILE) {
+         Inst<TX_WIDE, LY_WIDE, MODE_R2C, true>::reg(KIND_TILE_WIDE);
+         Inst<TX_WIDE, LY_WIDE, MODE_C2R, true>::reg(KIND_TILE_WIDE);
+      }
    }
 } registrar_instance;
 

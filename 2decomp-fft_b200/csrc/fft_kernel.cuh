@@ -55,6 +55,7 @@ struct FftArgs {
    int n;              // transform length (checked against the template)
    int backward;       // 1: conj-in / conj-out (isign=+1), C2C only
    int passthrough;    // 1: opt_skip_XYZ_c2c -- move data through the maps without transforming
+   int debug;          // experiments only (D2D_DEBUG_SKIP): bit 0 = drop the global stores, bit 1 = drop the global loads
    const void *tw;     // twiddle tables of this n / dtype
 };
 
@@ -244,7 +245,7 @@ template <typename T2> __device__ __forceinline__ void store_piece(const PieceMa
 }
 
 // One Stockham pass PASS on the registers of one thread (all loops are compile-time).
-template <typename T, class P, int PASS, int TX, int PADK> struct PassOp {
+template <typename T, class P, int PASS, int SP, int PADK, bool TWS> struct PassOp {
    using T2 = typename Vec2<T>::type;
    using PI = PlanInfo<P>;
    static constexpr int E = P::E, TPL = P::T, N = P::N;
@@ -258,7 +259,9 @@ template <typename T, class P, int PASS, int TX, int PADK> struct PassOp {
          const int q = (j + TPL * u) % NS;
 #pragma unroll
          for (int r = 1; r < R; r++) {
-            T2 w = ldg_nc(tw + PI::tw_off(PASS) + (r - 1) * NS + q);
+            T2 w;
+            if constexpr (TWS) w = tw[PI::tw_off(PASS) + (r - 1) * NS + q]; // table staged in shared memory
+            else w = ldg_nc(tw + PI::tw_off(PASS) + (r - 1) * NS + q);
             v[u + r * NB] = cmul(v[u + r * NB], w);
          }
       }
@@ -282,7 +285,7 @@ template <typename T, class P, int PASS, int TX, int PADK> struct PassOp {
          const int jj = j + TPL * u;
          const int base = (jj / NS) * (NS * R) + (jj % NS);
 #pragma unroll
-         for (int r = 0; r < R; r++) lsm[padix<PADK>(base + r * NS) * TX] = v[u + Bfly<T, R>::out_idx(r) * NB];
+         for (int r = 0; r < R; r++) lsm[padix<PADK>(base + r * NS) * SP] = v[u + Bfly<T, R>::out_idx(r) * NB];
       }
    }
    // last pass: put output slot s = u + r*NB into w[s] (compile-time permutation)
@@ -302,12 +305,12 @@ struct NoHook {
 // All passes.  SYNC0: a barrier is needed before the first scatter too (the exchange buffer was used
 // as the landing zone of this tile's input).  `hook` runs right after the LAST read of the exchange
 // buffer: the buffer is free from there on (the pipelined kernel starts the next tile's loads there).
-template <typename T, class P, int PASS, int TX, int PADK, bool SYNC0, class Hook> struct RunPasses {
+template <typename T, class P, int PASS, int SP, int PADK, bool TWS, bool SYNC0, class Hook> struct RunPasses {
    using T2 = typename Vec2<T>::type;
    using PI = PlanInfo<P>;
    static __device__ __forceinline__ void run(T2 *v, int j, T2 *lsm, const T2 *__restrict__ tw, Hook &hook)
    {
-      using Op = PassOp<T, P, PASS, TX, PADK>;
+      using Op = PassOp<T, P, PASS, SP, PADK, TWS>;
       Op::twiddle(v, j, tw);
       Op::butterflies(v);
       if constexpr (PASS + 1 < PI::npass) {
@@ -315,9 +318,9 @@ template <typename T, class P, int PASS, int TX, int PADK, bool SYNC0, class Hoo
          Op::scatter(v, j, lsm);
          __syncthreads();
 #pragma unroll
-         for (int s = 0; s < P::E; s++) v[s] = lsm[padix<PADK>(j + P::T * s) * TX];
+         for (int s = 0; s < P::E; s++) v[s] = lsm[padix<PADK>(j + P::T * s) * SP];
          if constexpr (PASS + 2 == PI::npass) hook();
-         RunPasses<T, P, PASS + 1, TX, PADK, SYNC0, Hook>::run(v, j, lsm, tw, hook);
+         RunPasses<T, P, PASS + 1, SP, PADK, TWS, SYNC0, Hook>::run(v, j, lsm, tw, hook);
       } else {
          T2 w[P::E];
          Op::unpermute(v, w);
@@ -327,12 +330,30 @@ template <typename T, class P, int PASS, int TX, int PADK, bool SYNC0, class Hoo
    }
 };
 
-template <typename T, class P, int TX, int LY, int PADK> struct KernelGeom {
+template <typename T, class P, int TX, int LY, int PADK, bool LM = false> struct KernelGeom {
    using T2 = typename Vec2<T>::type;
    static constexpr int threads = TX * LY * P::T;
-   static constexpr int line_sm = padix<PADK>(P::N - 1) + 1; // padded complex elements per line
-   static constexpr size_t smem_bytes = (size_t)line_sm * TX * LY * sizeof(T2);
+   // Two shared-memory layouts, chosen so that what is contiguous in global memory lands contiguously
+   // (LDGSTS moves 32-byte sectors; splitting one across distant shared addresses halves its rate,
+   // measured): LM = false, interleaved [position][tx] for tile-like inputs (TX adjacent lines are
+   // contiguous in memory); LM = true, line-major [tx][position] for line-like inputs (the transform
+   // axis is contiguous): line l of the block at l * line_sm, position p at padix(p).
+   // line_sm == bankq/TX (mod bankq = 128 B / sizeof(T2)) makes a quarter-warp (fp64) / half-warp (fp32)
+   // made of TX lines x bankq/TX consecutive positions hit distinct banks, for the tile-ordered lanes (tx fastest)
+   // as well as for the line-ordered lanes used to land line-like inputs.
+   static constexpr int bankq = 128 / (int)sizeof(T2);
+   static constexpr int line_raw = padix<PADK>(P::N - 1) + 1;
+   static constexpr int lane_step = (bankq / TX) > 1 ? (bankq / TX) : 1; // line_sm == lane_step (mod bankq)
+   static constexpr int line_sm = (TX > 1 && LM) ? ((line_raw + bankq - 1 - lane_step) / bankq * bankq + lane_step) : line_raw;
+   static constexpr size_t tile_bytes = (size_t)line_sm * TX * LY * sizeof(T2);
    static constexpr bool needs_smem = (PlanInfo<P>::npass > 1);
+   // twiddle tables live in shared memory when two blocks per SM still fit (L1 misses on the
+   // ld.global.nc path cost ~1.7x the data in L2 reads, measured)
+   static constexpr size_t tw_bytes = (size_t)PlanInfo<P>::tw_total * sizeof(T2);
+   static constexpr size_t kSmemPerSM = 227 * 1024;
+   static constexpr bool tw_in_smem = needs_smem && (tile_bytes + tw_bytes <= kSmemPerSM) &&
+                                      (kSmemPerSM / (tile_bytes + tw_bytes) == kSmemPerSM / tile_bytes || kSmemPerSM / (tile_bytes + tw_bytes) >= 2);
+   static constexpr size_t smem_bytes = tile_bytes + (tw_in_smem ? tw_bytes : 0);
 };
 
 // ---- cp.async (LDGSTS) helpers: global -> shared without a register round trip -------------------
@@ -361,11 +382,12 @@ __device__ __forceinline__ float flip_sign(float y, unsigned mask_hi) { return _
 // the kernel is software-pipelined: the input of tile i+1 is brought in with cp.async into the very
 // buffer tile i used for its exchanges, as soon as tile i has read it for the last time, and lands
 // while tile i runs its last pass and its stores.
-template <typename T, class P, int TX, int LY, int PADK, int MODE, bool PAIRVEC, int MINB>
+template <typename T, class P, int TX, int LY, int PADK, int MODE, bool PAIRVEC, int MINB, bool LM>
 __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_constant__ FftArgs g)
 {
    using T2 = typename Vec2<T>::type;
-   using G = KernelGeom<T, P, TX, LY, PADK>;
+   using G = KernelGeom<T, P, TX, LY, PADK, LM>;
+   constexpr int SP = LM ? 1 : TX; // shared-memory stride between consecutive positions of a line
    constexpr int N = P::N, E = P::E, TPL = P::T;
    constexpr bool PIPE = G::needs_smem && MODE != MODE_C2R;
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -378,49 +400,71 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
    const int tiles_a = (g.na + TX - 1) / TX;
    const long long ntiles = (long long)tiles_a * g.nb;
    const long long ngroups = (ntiles + LY - 1) / LY;
-   T2 *lsm = sm + (size_t)ly * (G::line_sm * TX) + tx;
+   T2 *lsm = LM ? sm + (size_t)(ly * TX + tx) * G::line_sm : sm + (size_t)ly * (G::line_sm * TX) + tx;
+   constexpr bool TWS = G::tw_in_smem;
    const T2 *__restrict__ tw = reinterpret_cast<const T2 *>(g.tw);
+   if constexpr (TWS) {
+      T2 *tws = sm + G::tile_bytes / sizeof(T2);
+      for (int i = tid; i < PlanInfo<P>::tw_total; i += TX * LY * TPL) tws[i] = ldg_nc(tw + i);
+      tw = tws;
+      __syncthreads();
+   }
    const unsigned conj_mask = g.backward ? 0x80000000u : 0u;
 
    long long a = 0, b = 0;
    bool valid = false, v1 = false;
+   // Staging identity.  cp.async only merges ADJACENT lanes into one L2 request (measured: a lane
+   // order that hops between lines costs 3.6x the requests and 2.6x the sectors), so the thread
+   // that brings an element in is chosen for coalescing, not for the butterflies: lanes run along
+   // the transform axis when the input is line-like (unit stride along e), along the tile axis
+   // otherwise.  When the two identities differ a barrier separates landing and reading back.
+   constexpr bool line_in = PIPE && TX > 1 && LM; // the host picks LM kernels for line-like inputs
+   const int stx = line_in ? (tid / TPL) % TX : tx;
+   const int sj = line_in ? tid % TPL : j;
+   T2 *slsm = LM ? sm + (size_t)(ly * TX + stx) * G::line_sm : sm + (size_t)ly * (G::line_sm * TX) + stx;
+   long long sa_ = 0;
+   bool svalid = false, sv1 = false;
    auto locate = [&](long long grp) {
       const long long tile = grp * LY + ly;
-      valid = tile < ntiles;
+      const bool in_range = tile < ntiles;
       b = tile / tiles_a;
-      a = (tile - b * tiles_a) * TX + tx;
-      valid = valid && (a < g.na);
+      const long long a0 = (tile - b * tiles_a) * TX;
+      a = a0 + tx;
+      sa_ = a0 + stx;
+      valid = in_range && (a < g.na);
       v1 = valid && (2 * a + 1 < g.na_real);
+      svalid = in_range && (sa_ < g.na);
+      sv1 = svalid && (2 * sa_ + 1 < g.na_real);
    };
 
-   // start the asynchronous loads of the current (a,b) line into its shared-memory slots
+   // start the asynchronous loads of the current tile into its shared-memory slots
    auto stage = [&]() {
       if constexpr (PIPE) {
-         if (valid) {
+         if (svalid && !(g.debug & 2)) {
             if constexpr (MODE == MODE_C2C) {
                if (g.in.np == 1) {
-                  const T2 *p = reinterpret_cast<const T2 *>(g.in.ptr[0]) + (long long)j * g.in.se[0] + a * g.in.sa[0] + b * g.in.sb[0];
+                  const T2 *p = reinterpret_cast<const T2 *>(g.in.ptr[0]) + (long long)sj * g.in.se[0] + sa_ * g.in.sa[0] + b * g.in.sb[0];
                   const long long step = (long long)TPL * g.in.se[0];
 #pragma unroll
-                  for (int s = 0; s < E; s++) cp_async<sizeof(T2)>(&lsm[padix<PADK>(j + TPL * s) * TX], p + s * step);
+                  for (int s = 0; s < E; s++) cp_async<sizeof(T2)>(&slsm[padix<PADK>(sj + TPL * s) * SP], p + s * step);
                } else {
 #pragma unroll
                   for (int s = 0; s < E; s++) {
                      int pc;
-                     const long long off = piece_addr(g.in, j + TPL * s, a, b, pc);
-                     cp_async<sizeof(T2)>(&lsm[padix<PADK>(j + TPL * s) * TX], reinterpret_cast<const T2 *>(g.in.ptr[pc]) + off);
+                     const long long off = piece_addr(g.in, sj + TPL * s, sa_, b, pc);
+                     cp_async<sizeof(T2)>(&slsm[padix<PADK>(sj + TPL * s) * SP], reinterpret_cast<const T2 *>(g.in.ptr[pc]) + off);
                   }
                }
             } else { // R2C: two real lines -> (re, im) of one complex line
-               const T *p = reinterpret_cast<const T *>(g.rptr) + (long long)j * g.rse + (2 * a) * g.rsa + b * g.rsb;
+               const T *p = reinterpret_cast<const T *>(g.rptr) + (long long)sj * g.rse + (2 * sa_) * g.rsa + b * g.rsb;
                const long long step = (long long)TPL * g.rse;
 #pragma unroll
                for (int s = 0; s < E; s++) {
-                  T2 *dst = &lsm[padix<PADK>(j + TPL * s) * TX];
+                  T2 *dst = &slsm[padix<PADK>(sj + TPL * s) * SP];
                   if constexpr (PAIRVEC) cp_async<sizeof(T2)>(dst, p + s * step);
                   else {
                      cp_async<sizeof(T)>(&dst->x, p + s * step);
-                     if (v1) cp_async<sizeof(T)>(&dst->y, p + s * step + g.rsa);
+                     if (sv1) cp_async<sizeof(T)>(&dst->y, p + s * step + g.rsa);
                   }
                }
             }
@@ -441,10 +485,11 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
 
       // ------------------------------------------------------------------ load
       if constexpr (PIPE) {
-         cp_async_wait_all(); // every thread reads back only what it staged itself: no barrier needed
+         cp_async_wait_all();
+         if (line_in) __syncthreads(); // staged by other threads (same identity otherwise: no barrier needed)
 #pragma unroll
          for (int s = 0; s < E; s++) {
-            T2 x = lsm[padix<PADK>(j + TPL * s) * TX];
+            T2 x = lsm[padix<PADK>(j + TPL * s) * SP];
             if constexpr (MODE == MODE_C2C) x.y = flip_sign(x.y, conj_mask);
             else if (!v1_cur) x.y = 0;
             v[s] = x;
@@ -481,8 +526,8 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
                if (v1_cur) B = load_piece<T2>(g.in, k, 2 * a_cur + 1, b_cur);
                if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
                if constexpr (G::needs_smem) {
-                  lsm[padix<PADK>(k) * TX] = T2{A.x - B.y, -(A.y + B.x)};
-                  if (k > 0 && 2 * k < N) lsm[padix<PADK>(N - k) * TX] = T2{A.x + B.y, A.y - B.x};
+                  lsm[padix<PADK>(k) * SP] = T2{A.x - B.y, -(A.y + B.x)};
+                  if (k > 0 && 2 * k < N) lsm[padix<PADK>(N - k) * SP] = T2{A.x + B.y, A.y - B.x};
                } else { // single-thread line (T == 1, j == 0, k == s): slots are the positions
                   v[s] = T2{A.x - B.y, -(A.y + B.x)};
                   if (s > 0 && 2 * s < N) v[(N - s) % E] = T2{A.x + B.y, A.y - B.x};
@@ -492,7 +537,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
          if constexpr (G::needs_smem) {
             __syncthreads();
 #pragma unroll
-            for (int s = 0; s < E; s++) v[s] = lsm[padix<PADK>(j + TPL * s) * TX];
+            for (int s = 0; s < E; s++) v[s] = lsm[padix<PADK>(j + TPL * s) * SP];
             __syncthreads();
          }
       }
@@ -512,10 +557,10 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
       // ------------------------------------------------------------------ transform
       if (!g.passthrough) {
          if constexpr (PIPE && MODE == MODE_C2C) {
-            RunPasses<T, P, 0, TX, PADK, true, decltype(prefetch_next)>::run(v, j, lsm, tw, prefetch_next);
+            RunPasses<T, P, 0, SP, PADK, TWS, true, decltype(prefetch_next)>::run(v, j, lsm, tw, prefetch_next);
          } else {
             NoHook nh;
-            RunPasses<T, P, 0, TX, PADK, PIPE, NoHook>::run(v, j, lsm, tw, nh);
+            RunPasses<T, P, 0, SP, PADK, TWS, PIPE, NoHook>::run(v, j, lsm, tw, nh);
          }
       } else if constexpr (PIPE && MODE == MODE_C2C) {
          prefetch_next();
@@ -523,7 +568,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
 
       // ------------------------------------------------------------------ store
       if constexpr (MODE == MODE_C2C) {
-         if (valid_cur) {
+         if (valid_cur && !(g.debug & 1)) {
             if (g.out.np == 1) {
                T2 *p = reinterpret_cast<T2 *>(g.out.ptr[0]) + (long long)j * g.out.se[0] + a_cur * g.out.sa[0] + b_cur * g.out.sb[0];
                const long long step = (long long)TPL * g.out.se[0];
@@ -559,7 +604,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
          if constexpr (G::needs_smem) {
             __syncthreads();
 #pragma unroll
-            for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * TX] = v[s];
+            for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * SP] = v[s];
             __syncthreads();
          }
          T2 zn[E / 2 + 1];
@@ -568,7 +613,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel(const __grid_co
             const int k = j + TPL * s;
             zn[s] = T2{0, 0};
             if (k <= N / 2 && (s < E / 2 || j == 0)) {
-               if constexpr (G::needs_smem) zn[s] = lsm[padix<PADK>((N - k) % N) * TX];
+               if constexpr (G::needs_smem) zn[s] = lsm[padix<PADK>((N - k) % N) * SP];
                else zn[s] = v[(N - s) % N]; // T == 1: k == s
             }
          }

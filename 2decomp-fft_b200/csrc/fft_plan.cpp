@@ -6,6 +6,7 @@
 // differs is the data path: each 1-D stage reads through a receive-layout piece map and writes
 // through a send-layout piece map, so the transposes shrink to the bare exchange.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -39,6 +40,8 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    g.out = out;
    g.backward = backward;
    g.passthrough = passthrough;
+   static const int dbg = getenv("D2D_DEBUG_SKIP") ? atoi(getenv("D2D_DEBUG_SKIP")) : 0;
+   g.debug = dbg;
    int kind;
    if (chain) {
       fft_stage_batch(dc, pencil, g.na, g.nb);
@@ -72,12 +75,19 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    }
    g.n = n;
    if (lines == 0) return;
-   const FftKernelInfo *k = fft_find(n, f64, kind, mode, pairvec);
+   const FftKernelInfo *k = nullptr;
+   static const bool wide = getenv("D2D_WIDE_REAL_TILES") && atoi(getenv("D2D_WIDE_REAL_TILES")) != 0;
+   if (wide && chain && mode != MODE_C2C && pencil == 2 && pairvec) k = fft_find(n, f64, KIND_TILE_WIDE, mode, pairvec);
+   // inputs that are contiguous along the transform axis land through the line-major kernels
+   const bool line_like = kind == KIND_TILE && ((mode == MODE_C2C && in.se[0] == 1) || (mode == MODE_R2C && g.rse == 1));
+   if (!k && line_like) k = fft_find(n, f64, kind, mode, pairvec, 1);
+   if (!k) k = fft_find(n, f64, kind, mode, pairvec);
    D2D_REQUIRE(k != nullptr, "transform length " + std::to_string(n) + " is not supported by the compiled kernels");
    g.tw = twiddles_for(ctx->device, n, f64);
    static const char *axes = "xyz";
    char label[32];
-   snprintf(label, sizeof(label), "fft_%s_%c", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil]);
+   snprintf(label, sizeof(label), "fft_%s_%c%s", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil],
+            (mode == MODE_C2C && chain) ? (backward ? "_bwd" : "_fwd") : "");
    ProfScope ps(ctx, label, bytes);
    cudaError_t e = k->launch(g, ctx->stream);
    if (e != cudaSuccess) throw Error(1000 + (int)e, std::string("FFT kernel launch failed: ") + cudaGetErrorString(e));
@@ -99,8 +109,10 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
 {
    Ctx *ctx = p.ctx;
    const int es = p.f64 ? 16 : 8;
-   const size_t wbytes = (size_t)es * dc.max_pencil();
-   const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C;
+   const int padq = 128 / es;
+   const size_t wbytes = (size_t)es * fft_work_elems(dc, padq);
+   // `out` can stand in for the first work buffer only when the padded wire layout fits in it
+   const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C && wbytes <= (size_t)es * dc.pencil_elems(st[2].pencil);
    int live_a = -1, live_b = -1; // work buffers holding the current stage's input
    auto pick = [&]() {
       for (int i = 0; i < 3; i++)
@@ -122,7 +134,7 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
       } else {
          if (s == 0 && borrow_out) sendbuf = out;
          else { send_w = pick(); sendbuf = ctx->reserve(send_w, wbytes); }
-         om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false);
+         om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false, padq);
       }
       run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
       if (last) break;
@@ -136,9 +148,9 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
          int recv_w = (old_a >= 0 && old_a != send_w) ? old_a : (old_b >= 0 && old_b != send_w) ? old_b : pick();
          recvbuf = ctx->reserve(recv_w, wbytes);
          live_b = recv_w;
-         exchange(ctx, dc, pen, nxt, sendbuf, recvbuf, es);
+         fft_exchange(ctx, dc, pen, nxt, sendbuf, recvbuf, es, padq);
       }
-      cur = fft_link_map(dc, nxt, pen, recvbuf, sendbuf, es, true);
+      cur = fft_link_map(dc, nxt, pen, recvbuf, sendbuf, es, true, padq);
    }
 }
 
@@ -146,7 +158,7 @@ static void reserve_all(Plan &p)
 {
    // grow the context's work buffers once, at plan time (never inside the timed path)
    const int es = p.f64 ? 16 : 8;
-   const size_t wb = (size_t)es * std::max(p.sp.d.max_pencil(), p.ph.d.max_pencil());
+   const size_t wb = (size_t)es * std::max(fft_work_elems(p.sp.d, 128 / es), fft_work_elems(p.ph.d, 128 / es));
    const bool multi = p.ctx->nranks > 1;
    p.ctx->reserve(0, wb);
    p.ctx->reserve(1, wb);

@@ -7,10 +7,10 @@
 
 namespace d2d {
 
-enum FftKind { KIND_LINE = 0 /* TX = 1, contiguous lines */, KIND_TILE = 1 /* TX > 1, strided lines */ };
+enum FftKind { KIND_LINE = 0 /* TX = 1, contiguous lines */, KIND_TILE = 1 /* TX > 1, strided lines */, KIND_TILE_WIDE = 2 /* 2x wider tile rows */ };
 
 struct FftKernelInfo {
-   int n, f64, kind, mode, pairvec;
+   int n, f64, kind, mode, pairvec, line_in; // line_in: shared memory laid out for inputs contiguous along the transform axis
    int tx, ly, threads, minb;
    size_t smem;
    int tw_total;                 // complex twiddle entries expected in FftArgs::tw
@@ -21,7 +21,7 @@ struct FftKernelInfo {
 
 void fft_register(const FftKernelInfo &);
 // exact lookup; nullptr if this (n, dtype, kind, mode, pairvec) was not compiled
-const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec);
+const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, int line_in = 0);
 int fft_registry_size();
 const FftKernelInfo *fft_registry_at(int i);
 

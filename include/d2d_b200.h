@@ -143,9 +143,11 @@ int d2d_fft_kernel_describe(int i, char *buf, int buflen);
  * producer (consumer = 0) or consumer (1).  Element e of line (a,b) lives at element offset
  * off[m] + (e - e0[m]) se[m] + a sa[m] + b sb[m] of the peers' buffer (in_self[m] = 0: the receive
  * buffer for a consumer, the send buffer for a producer) or of the buffer holding this rank's own
- * block (in_self[m] = 1: always the producer's send buffer).  na/nb = batch extents of the stage. */
-int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int *np, int e0[9], int64_t off[8],
-                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb);
+ * block (in_self[m] = 1: always the producer's send buffer).  na/nb = batch extents of the stage;
+ * cnt/disp = this side's block sizes / displacements (blocks are padded to `padq` elements along
+ * their unit-stride axis, so these are NOT the reference's x1cnts... tables). */
+int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int padq, int *np, int e0[9], int64_t off[8],
+                       int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb, int64_t cnt[8], int64_t disp[8]);
 /* the user's dense pencil seen with the same (a,b) convention */
 int d2d_debug_user_map(const d2d_decomp *decomp, int pencil, int64_t *se, int64_t *sa, int64_t *sb, int *n, int *na, int *nb);
 

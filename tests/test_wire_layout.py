@@ -1,7 +1,8 @@
 """CPU emulation of the private wire layouts used inside decomp_2d_fft_3d (no GPU): a producer
-stage writes its pencil through its link map, the all-to-all-v moves the blocks with the reference's
-counts / displacements, the consumer stage gathers through its link map -- and must see exactly the
-destination pencil of the reference transpose (oracle), for every link direction, ragged grids included."""
+stage writes its pencil through its link map, the all-to-all-v moves the (padded) blocks with the
+library's own counts / displacements, the consumer stage gathers through its link map -- and must
+see exactly the destination pencil of the reference transpose (oracle), for every link direction,
+ragged grids and both paddings (fp64: 8 elements = 128 B, fp32: 16 elements) included."""
 import ctypes as C
 
 import numpy as np
@@ -13,17 +14,18 @@ from util import pkg
 AXES = {0: (0, 1, 2), 1: (1, 2, 0), 2: (2, 0, 1)}  # stage pencil -> (axis of e, axis of a, axis of b)
 
 
-def link_map(p, dec, pencil, other, consumer):
+def link_map(p, dec, pencil, other, consumer, padq):
     lib = p.lib()
     np_, na, nb = C.c_int(), C.c_int(), C.c_int()
     e0 = (C.c_int * 9)()
-    off, se, sa, sb = [(C.c_int64 * 8)() for _ in range(4)]
+    off, se, sa, sb, cnt, disp = [(C.c_int64 * 8)() for _ in range(6)]
     in_self = (C.c_int * 8)()
-    rc = lib.d2d_debug_link_map(dec._h, pencil, other, consumer, C.byref(np_), e0, off, in_self, se, sa, sb, C.byref(na), C.byref(nb))
+    rc = lib.d2d_debug_link_map(dec._h, pencil, other, consumer, padq, C.byref(np_), e0, off, in_self, se, sa, sb, C.byref(na),
+                                C.byref(nb), cnt, disp)
     assert rc == 0, lib.d2d_last_error()
     n = np_.value
     return dict(np=n, e0=list(e0)[: n + 1], off=list(off)[:n], in_self=list(in_self)[:n], se=list(se)[:n], sa=list(sa)[:n],
-                sb=list(sb)[:n], na=na.value, nb=nb.value)
+                sb=list(sb)[:n], na=na.value, nb=nb.value, cnt=list(cnt)[:n], disp=list(disp)[:n])
 
 
 def offsets(m, e, a, b):
@@ -35,10 +37,11 @@ def offsets(m, e, a, b):
     return off, np.array(m["in_self"])[piece]
 
 
+@pytest.mark.parametrize("padq", [8, 16, 1])
 @pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (3, 2), (4, 2)])
 @pytest.mark.parametrize("shape", [(17, 13, 11), (32, 16, 33), (9, 24, 16)])
 @pytest.mark.parametrize("link", [(0, 1), (1, 0), (1, 2), (2, 1)])
-def test_link_maps_compose_to_the_reference_transpose(shape, grid, link):
+def test_link_maps_compose_to_the_reference_transpose(shape, grid, link, padq):
     p = pkg()
     P, Q = link
     nranks = grid[0] * grid[1]
@@ -48,43 +51,42 @@ def test_link_maps_compose_to_the_reference_transpose(shape, grid, link):
     want = orc.scatter(g, grid, Q)
     decs = [p.DecompInfo.for_rank(nx, ny, nz, grid[0], grid[1], r) for r in range(nranks)]
     col = (P == 0 or Q == 0)
-
-    def tables(d, pen, oth):
-        if pen == 0:
-            return d.x1cnts, d.x1disp
-        if pen == 2:
-            return d.z2cnts, d.z2disp
-        return (d.y1cnts, d.y1disp) if oth == 0 else (d.y2cnts, d.y2disp)
-
+    prod = [link_map(p, decs[r], P, Q, 0, padq) for r in range(nranks)]
+    cons = [link_map(p, decs[r], Q, P, 1, padq) for r in range(nranks)]
     sendbufs, recvbufs = [], []
     for r in range(nranks):
-        m = link_map(p, decs[r], P, Q, 0)
+        m = prod[r]
         sz = (decs[r].xsz, decs[r].ysz, decs[r].zsz)[P]
         ax = AXES[P]
         assert (m["na"], m["nb"]) == (sz[ax[1]], sz[ax[2]])
         idx = np.indices(sz)
         e, a, b = idx[ax[0]].ravel(), idx[ax[1]].ravel(), idx[ax[2]].ravel()
         off, sel = offsets(m, e, a, b)
-        assert np.all(sel == (np.searchsorted(np.array(m["e0"][1:]), e, side="right") == (r // grid[1] if col else r % grid[1])))
-        buf = np.full(int(np.prod(sz)), np.nan)
-        assert len(np.unique(off)) == len(off) and off.min() == 0 and off.max() == len(buf) - 1, "producer map must be a bijection"
-        buf[off] = src[r].ravel(order="C")[np.ravel_multi_index((idx[0].ravel(), idx[1].ravel(), idx[2].ravel()), sz)]
+        total = m["disp"][-1] + m["cnt"][-1]
+        assert total >= int(np.prod(sz)) and (padq > 1 or total == int(np.prod(sz)))
+        assert len(np.unique(off)) == len(off) and off.min() >= 0 and off.max() < total, "producer map must be injective"
+        # rows of every block start on a padq boundary
+        rows = off[e == np.array(m["e0"])[np.minimum(np.searchsorted(np.array(m["e0"][1:]), e, side="right"), m["np"] - 1)]]
+        if padq > 1 and min(m["se"]) == 1:
+            assert np.all(rows % padq == 0)
+        buf = np.full(total, np.nan)
+        buf[off] = src[r][idx[0].ravel(), idx[1].ravel(), idx[2].ravel()]
         sendbufs.append(buf)
-        recvbufs.append(np.full(int(np.prod((decs[r].xsz, decs[r].ysz, decs[r].zsz)[Q])), np.nan))
-    # all-to-all-v with the reference's counts / displacements (self block excluded: it never moves)
+        recvbufs.append(np.full(cons[r]["disp"][-1] + cons[r]["cnt"][-1], np.nan))
+    # all-to-all-v with the library's counts / displacements (self block excluded: it never moves)
     for r in range(nranks):
         c1, c2 = r // grid[1], r % grid[1]
         me = c1 if col else c2
-        rc, rd = tables(decs[r], Q, P)
         for mth in range(grid[0] if col else grid[1]):
             if mth == me:
                 continue
             peer = (mth * grid[1] + c2) if col else (c1 * grid[1] + mth)
-            sc, sd = tables(decs[peer], P, Q)
-            assert sc[me] == rc[mth]
-            recvbufs[r][rd[mth]: rd[mth] + rc[mth]] = sendbufs[peer][sd[me]: sd[me] + sc[me]]
+            sc, sd = prod[peer]["cnt"][me], prod[peer]["disp"][me]
+            rc, rd = cons[r]["cnt"][mth], cons[r]["disp"][mth]
+            assert sc == rc, "send / recv block sizes must agree"
+            recvbufs[r][rd: rd + rc] = sendbufs[peer][sd: sd + sc]
     for r in range(nranks):
-        m = link_map(p, decs[r], Q, P, 1)
+        m = cons[r]
         sz = (decs[r].xsz, decs[r].ysz, decs[r].zsz)[Q]
         ax = AXES[Q]
         idx = np.indices(sz)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--shape", default=None, help="nx,ny,nz (default n,n,n)")
     ap.add_argument("--only1d", action="store_true")
     ap.add_argument("--axes", default="0,1,2")
+    ap.add_argument("--oop", action="store_true", help="1-D stages out of place")
     ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     p = package()
@@ -39,15 +40,16 @@ def main():
     nx, ny, nz = shape
     cz = d2d.alloc_x(cdt)  # (nx,ny,nz) complex
     cz.real.normal_()
+    co = d2d.alloc_x(cdt) if a.oop else None
     res = {}
     for axis in [int(x) for x in a.axes.split(',')]:
         for _ in range(a.warm):
-            d2d.c2c_1m(cz, axis, -1)
+            d2d.c2c_1m(cz, axis, -1, out=co)
         d2d.sync()
         d2d.profile_reset()
         d2d.profile(True)
         for _ in range(a.reps):
-            d2d.c2c_1m(cz, axis, -1)
+            d2d.c2c_1m(cz, axis, -1, out=co)
         d2d.sync()
         d2d.profile(False)
         for k, (ms, calls, by) in d2d.profile_read().items():
