@@ -446,7 +446,7 @@ int d2d_fft_kernel_describe(int i, char *buf, int buflen)
    if (i < 0 || i >= fft_registry_size()) return 1;
    const FftKernelInfo *k = fft_registry_at(i);
    snprintf(buf, buflen, "n=%d %s %s %s pairvec=%d tx=%d ly=%d threads=%d minb=%d smem=%zu radices=%d,%d,%d,%d", k->n,
-            k->f64 ? "f64" : "f32", k->kind == KIND_LINE ? "line" : "tile",
+            k->f64 ? "f64" : "f32", k->v2 ? (k->inl == IN_TILE ? "v2-tma-tile" : "v2-tma-line") : k->kind == KIND_LINE ? "line" : "tile",
             k->mode == MODE_C2C ? "c2c" : k->mode == MODE_R2C ? "r2c" : "c2r", k->pairvec, k->tx, k->ly, k->threads, k->minb,
             k->smem, k->radix[0], k->radix[1], k->radix[2], k->radix[3]);
    return 0;

@@ -144,7 +144,7 @@ struct CopyArgs {
 void launch_copy(Ctx *ctx, const CopyArgs &c, int es);
 
 // ---- twiddles -----------------------------------------------------------------------------------
-const void *twiddles_for(int device, int n, int f64);
+const void *twiddles_for(int device, int n, int f64, int compact = 0);
 void twiddles_release_all();
 
 inline int elem_size(int dtype, int is_complex) { return (dtype == D2D_F64 ? 8 : 4) * (is_complex ? 2 : 1); }

@@ -25,7 +25,13 @@ void fft_register(const FftKernelInfo &k) { registry().push_back(k); }
 const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, int line_in)
 {
    for (const auto &k : registry())
-      if (k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec && k.line_in == line_in) return &k;
+      if (!k.v2 && k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec && k.line_in == line_in) return &k;
+   return nullptr;
+}
+const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl)
+{
+   for (const auto &k : registry())
+      if (k.v2 && k.n == n && k.f64 == f64 && k.mode == mode && k.inl == inl) return &k;
    return nullptr;
 }
 int fft_registry_size() { return (int)registry().size(); }
@@ -41,36 +47,36 @@ std::mutex g_tw_mutex;
 std::map<TwKey, void *> g_tw;
 } // namespace
 
-const void *twiddles_for(int device, int n, int f64)
+const void *twiddles_for(int device, int n, int f64, int compact)
 {
+   // compact = 1: the v2 layout (fft_kernel_v2.cuh PlanInfo2): radix-2/4 passes keep only the r = 1 row
    std::lock_guard<std::mutex> lk(g_tw_mutex);
-   TwKey key{device, n, f64};
+   TwKey key{device, n, f64 + 2 * compact};
    auto it = g_tw.find(key);
    if (it != g_tw.end()) return it->second;
    const FftKernelInfo *k = nullptr;
    for (int i = 0; i < fft_registry_size(); i++)
-      if (fft_registry_at(i)->n == n && fft_registry_at(i)->f64 == f64) { k = fft_registry_at(i); break; }
+      if (fft_registry_at(i)->n == n && fft_registry_at(i)->f64 == f64 && fft_registry_at(i)->v2 == compact) { k = fft_registry_at(i); break; }
    D2D_REQUIRE(k != nullptr, "no FFT kernel compiled for this length");
-   const int total = std::max(1, k->tw_total);
-   std::vector<double> hd((size_t)2 * total, 0.0);
-   size_t pos = 0;
+   std::vector<double> hd;
    long long ns = 1;
    for (int p = 0; p < k->npass; p++) {
       const int R = k->radix[p];
       if (p >= 1) {
-         for (int r = 1; r < R; r++)
+         const int rmax = (compact && R <= 4) ? 1 : R - 1;
+         for (int r = 1; r <= rmax; r++)
             for (long long q = 0; q < ns; q++) {
                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(r * q) / (long double)(ns * R);
-               hd[2 * pos] = (double)cosl(ang);
-               hd[2 * pos + 1] = (double)sinl(ang);
-               pos++;
+               hd.push_back((double)cosl(ang));
+               hd.push_back((double)sinl(ang));
             }
       }
       ns *= R;
    }
-   D2D_REQUIRE((int)pos == k->tw_total, "twiddle table size mismatch");
+   D2D_REQUIRE((int)(hd.size() / 2) == k->tw_total, "twiddle table size mismatch");
+   if (hd.empty()) hd.resize(2, 0.0);
    void *dptr = nullptr;
-   const size_t bytes = (size_t)total * (f64 ? 16 : 8);
+   const size_t bytes = (hd.size() / 2) * (f64 ? 16 : 8);
    D2D_CHECK_CUDA(cudaMalloc(&dptr, bytes));
    if (f64) {
       D2D_CHECK_CUDA(cudaMemcpy(dptr, hd.data(), bytes, cudaMemcpyHostToDevice));

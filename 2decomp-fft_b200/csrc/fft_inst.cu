@@ -84,9 +84,70 @@ template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
    }
 };
 
+// ---- v2: TMA-staged kernels (fft_kernel_v2.cuh) --------------------------------------------------
+constexpr int TX2 = 64 / (int)sizeof(T2);                                  // 64-byte tile rows
+constexpr int LY2 = cmax(1, kTargetThreads / (TX2 * P::T));
+constexpr size_t kSmemSM = 227 * 1024;
+
+template <int MODE, int INL> struct Inst2 {
+   using G = Geom2<real_t, P, TX2, LY2, PADK, MODE, INL>;
+   static constexpr bool fits = PlanInfo<P>::npass >= 2 && P::N >= 256 && G::late_fits && G::threads <= 1024 && G::smem_bytes + 1024 <= kSmemSM;
+   static constexpr int MINB = (G::threads <= 256 && 2 * (G::smem_bytes + 1024) <= kSmemSM) ? 2 : 1;
+   static cudaError_t launch(const FftArgs2 &g, const TmapPack &tm, cudaStream_t st)
+   {
+      auto kern = fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB>;
+      static bool attr_done = false;
+      static int resident = 0;
+      const size_t smem = G::smem_bytes;
+      if (!attr_done) {
+         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+         if (e != cudaSuccess) return e;
+         int dev = 0, sms = 0, per_sm = 0;
+         e = cudaGetDevice(&dev);
+         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
+         if (e != cudaSuccess) return e;
+         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+         resident = sms * per_sm;
+         attr_done = true;
+      }
+      const long long tiles = (long long)((g.a.na + TX2 - 1) / TX2) * g.a.nb;
+      const long long groups = (tiles + LY2 - 1) / LY2;
+      if (groups <= 0) return cudaSuccess;
+      const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
+      kern<<<blocks, G::threads, smem, st>>>(g, tm);
+      return cudaGetLastError();
+   }
+   static void reg()
+   {
+      if constexpr (fits) {
+         using PI = PlanInfo<P>;
+         FftKernelInfo k{};
+         k.n = P::N; k.f64 = D2D_F64; k.kind = KIND_TILE; k.mode = MODE; k.pairvec = 0;
+         k.tx = TX2; k.ly = LY2; k.threads = G::threads; k.minb = MINB;
+         k.smem = G::smem_bytes;
+         k.tw_total = PlanInfo2<P>::tw_total; k.npass = PI::npass;
+         for (int p = 0; p < 4; p++) k.radix[p] = PI::radix(p);
+         k.func = (const void *)fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB>;
+         k.line_in = INL == IN_LINE;
+         k.launch = nullptr;
+         k.v2 = 1; k.inl = INL;
+         k.rows = G::rows; k.rows_early = G::rows_early; k.row_bytes = G::row_bytes;
+         k.launch2 = &launch;
+         fft_register(k);
+      }
+   }
+};
+
 struct Registrar {
    Registrar()
    {
+      Inst2<MODE_C2C, IN_TILE>::reg();
+      Inst2<MODE_C2C, IN_LINE>::reg();
+      Inst2<MODE_R2C, IN_TILE>::reg();
+      Inst2<MODE_R2C, IN_LINE>::reg();
+      Inst2<MODE_C2R, IN_TILE>::reg();
+      Inst2<MODE_C2R, IN_LINE>::reg();
       Inst<1, LY_LINE, MODE_C2C, false>::reg(KIND_LINE);
       Inst<1, LY_LINE, MODE_R2C, false>::reg(KIND_LINE);
       Inst<1, LY_LINE, MODE_C2R, false>::reg(KIND_LINE);

@@ -1,0 +1,481 @@
+// fft_kernel_v2.cuh -- TMA-staged, double-landing variant of the batched 1-D FFT kernel (sm_100a).
+//
+// Same arithmetic as fft_kernel.cuh (Stockham passes, register butterflies, padded shared-memory
+// exchange buffer X) and the same fused pack/unpack through piece maps on the store side; what
+// changes is how a tile reaches the SM:
+//
+//   * the input of a tile is brought in by the TMA engine, not by LSU instructions:
+//       IN_TILE  strided pencils (TX adjacent lines are contiguous in memory): cp.async.bulk.tensor
+//                3-D boxes {TX lines x <=256 rows x 1} described by tensor maps built on the host,
+//                one per piece of the receive layout; out-of-range lines are zero-filled by the
+//                hardware, so ragged batch extents need no special code;
+//       IN_LINE  lines contiguous along the transform axis: one cp.async.bulk (1-D) per line piece;
+//     completion is tracked by two mbarriers (complete_tx::bytes);
+//   * the landing zone of the FIRST half of a tile (buffer L) is separate from the exchange buffer,
+//     so the first half of tile i+1 is requested as soon as tile i sits in registers and has the
+//     whole tile period to arrive; the SECOND half lands in the exchange buffer itself once tile i
+//     has read it for the last time (as in v1).  Two resident blocks per SM still fit
+//     (N = 1024 fp64: 32 KB L + 69.6 KB X + 7.8 KB twiddles).
+//   * twiddle tables of radix-2/4 passes keep only W^q; W^2q and W^3q are formed by multiplication
+//     (saves 8 KB of shared memory at N = 1024, which is what lets L fit).
+//   * c2r is pipelined like the other modes: the two Hermitian half-lines of a pair land raw and
+//     are combined while being read into registers.
+//
+// Replaces the same reference code as fft_kernel.cuh: the cuFFT executions of src/fft_cufft.f90:489-671
+// and mem_split_* / mem_merge_* of src/transpose_*.f90.
+#pragma once
+#include <cuda.h>
+
+#include "fft_kernel.cuh"
+
+namespace d2d {
+
+enum InLayout { IN_TILE = 0, IN_LINE = 1 };
+
+constexpr int kMaxTmaps = 16;
+constexpr int kMaxLoadOps = 40;
+
+struct LoadOp {
+   short map;     // index into TmapPack::m
+   short late;    // bit 0: 0 lands in L (first rows), 1 lands in the exchange buffer (last rows); bit 1: tensor dims are (a, b, e)
+   int c1;        // row coordinate inside the piece's tensor
+   int dst_row;   // landing row relative to the start of its zone
+   int bytes;     // box bytes (expect_tx bookkeeping)
+};
+
+struct alignas(64) TmapPack {
+   CUtensorMap m[kMaxTmaps];
+};
+
+struct FftArgs2 {
+   FftArgs a;
+   int nops;
+   int c0_mul;               // dim-0 coordinate of a tile = a0 * c0_mul (scalars per line along dim 0)
+   int bytes_early, bytes_late; // per sub-tile
+   LoadOp ops[kMaxLoadOps];
+};
+
+// ---- twiddle layout with compact radix-2/4 tables ---------------------------------------------------
+template <class P> struct PlanInfo2 {
+   using PI = PlanInfo<P>;
+   static constexpr bool compact(int p) { return p >= 1 && PI::radix(p) <= 4; }
+   static constexpr int entries(int p) { return p < 1 ? 0 : (compact(p) ? PI::ns(p) : (PI::radix(p) - 1) * PI::ns(p)); }
+   static constexpr int tw_off(int p) { return p <= 1 ? 0 : tw_off(p - 1) + entries(p - 1); }
+   static constexpr int tw_total = tw_off(PI::npass);
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+   asm volatile("{\n"
+                ".reg .pred p;\n"
+                "WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra DONE_%=;\n"
+                "bra WAIT_%=;\n"
+                "DONE_%=:\n"
+                "}\n" ::"r"(smem_u32(bar)),
+                "r"(parity)
+                : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, void *bar)
+{
+   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(dst)),
+                "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, void *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+                "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
+
+// One pass with the compact twiddle layout (otherwise PassOp's).
+template <typename T, class P, int PASS, int SP, int PADK> struct PassOp2 : PassOp<T, P, PASS, SP, PADK, true> {
+   using Base = PassOp<T, P, PASS, SP, PADK, true>;
+   using T2 = typename Vec2<T>::type;
+   using PI = PlanInfo<P>;
+   using PI2 = PlanInfo2<P>;
+   static __device__ __forceinline__ void twiddle(T2 *v, int j, const T2 *__restrict__ tw)
+   {
+      if (PASS == 0) return;
+      constexpr int R = Base::R, NS = Base::NS, NB = Base::NB, TPL = Base::TPL;
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+         const int q = (j + TPL * u) % NS;
+         if constexpr (PI2::compact(PASS)) {
+            const T2 w1 = tw[PI2::tw_off(PASS) + q];
+            v[u + NB] = cmul(v[u + NB], w1);
+            if constexpr (R == 4) {
+               const T2 w2 = cmul(w1, w1);
+               const T2 w3 = cmul(w2, w1);
+               v[u + 2 * NB] = cmul(v[u + 2 * NB], w2);
+               v[u + 3 * NB] = cmul(v[u + 3 * NB], w3);
+            }
+         } else {
+#pragma unroll
+            for (int r = 1; r < R; r++) v[u + r * NB] = cmul(v[u + r * NB], tw[PI2::tw_off(PASS) + (r - 1) * NS + q]);
+         }
+      }
+   }
+};
+
+// All passes.  The caller has put a block barrier between the landing reads and this call, so the
+// first scatter needs none; `late` runs right after the LAST read of the exchange buffer.
+template <typename T, class P, int PASS, int SP, int PADK, class Late> struct RunPasses2 {
+   using T2 = typename Vec2<T>::type;
+   using PI = PlanInfo<P>;
+   static __device__ __forceinline__ void run(T2 *v, int j, T2 *lsm, const T2 *__restrict__ tw, Late &late)
+   {
+      using Op = PassOp2<T, P, PASS, SP, PADK>;
+      Op::twiddle(v, j, tw);
+      Op::butterflies(v);
+      if constexpr (PASS + 1 < PI::npass) {
+         if (PASS > 0) __syncthreads();
+         Op::scatter(v, j, lsm);
+         __syncthreads();
+#pragma unroll
+         for (int s = 0; s < P::E; s++) v[s] = lsm[padix<PADK>(j + P::T * s) * SP];
+         if constexpr (PASS + 2 == PI::npass) late();
+         RunPasses2<T, P, PASS + 1, SP, PADK, Late>::run(v, j, lsm, tw, late);
+      } else {
+         T2 w[P::E];
+         Op::unpermute(v, w);
+#pragma unroll
+         for (int s = 0; s < P::E; s++) v[s] = w[s];
+      }
+   }
+};
+
+// ---- geometry ---------------------------------------------------------------------------------------
+template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> struct Geom2 {
+   using T2 = typename Vec2<T>::type;
+   static constexpr int N = P::N, NH = N / 2 + 1;
+   static constexpr int threads = TX * LY * P::T;
+   static constexpr int bankq = 128 / (int)sizeof(T2);
+   // exchange buffer: interleaved [padix(position)][tx] per sub-tile (v1's tile layout)
+   static constexpr int x_line = padix<PADK>(N - 1) + 1;
+   static constexpr size_t x_sub = ((size_t)x_line * TX * sizeof(T2) + 127) / 128 * 128; // bytes per sub-tile (TMA lands on 128-byte boundaries)
+   static constexpr size_t x_bytes = x_sub * LY;
+   // landing geometry.  "rows" run along the transform axis for IN_TILE, lines are whole for IN_LINE.
+   //   IN_TILE : row = ROWU scalars-of-16-bytes... expressed in bytes below
+   //   C2C     : row = TX complex              rows = N
+   //   R2C     : row = TX real pairs           rows = N
+   //   C2R     : row = 2 TX complex            rows = NH
+   static constexpr int rows = (MODE == MODE_C2R) ? NH : N;
+   static constexpr int row_bytes = (MODE == MODE_C2R ? 2 : 1) * TX * (int)sizeof(T2);
+   static constexpr int rows_early = (MODE == MODE_C2R) ? N / 4 : N / 2; // boxes never straddle this row
+   // IN_LINE: lines per sub-tile and their shared-memory pitch (bytes)
+   //   C2C : TX complex lines of N;  R2C : 2 TX real lines of N;  C2R : 2 TX complex half-lines of NH
+   static constexpr int nlines = (MODE == MODE_C2C) ? TX : 2 * TX;
+   static constexpr int lines_early = nlines / 2;
+   static constexpr int line_elems = (MODE == MODE_C2R) ? NH : N;                       // elements per line
+   static constexpr int line_esize = (MODE == MODE_R2C) ? (int)sizeof(T) : (int)sizeof(T2);
+   // pitch chosen so that the TX lines read by a quarter/half warp fall into distinct banks
+   static constexpr int line_pitch_elems = (MODE == MODE_C2C)   ? N + (bankq / TX > 0 ? bankq / TX : 1)
+                                           : (MODE == MODE_R2C) ? N + 16 / (int)sizeof(T) * (TX >= 4 ? 2 : 4)
+                                                                : NH;
+   static constexpr size_t line_pitch = ((size_t)line_pitch_elems * line_esize + 15) / 16 * 16;
+   static constexpr size_t l_sub = (((INL == IN_TILE) ? (size_t)rows_early * row_bytes : (size_t)lines_early * line_pitch) + 127) / 128 * 128;
+   static constexpr size_t late_sub = (INL == IN_TILE) ? (size_t)(rows - rows_early) * row_bytes : (size_t)(nlines - lines_early) * line_pitch;
+   static constexpr size_t l_bytes = l_sub * LY;
+   static constexpr int late_skew = (INL == IN_LINE && MODE == MODE_C2C) ? (bankq / 2) * (int)sizeof(T2) : 0; // bank skew of the late zone
+   static constexpr bool late_fits = late_sub + late_skew <= x_sub; // the late half of a tile lands in the exchange buffer of its sub-tile
+   static constexpr size_t tw_bytes = ((size_t)PlanInfo2<P>::tw_total * sizeof(T2) + 15) / 16 * 16;
+   static constexpr size_t off_x = l_bytes;
+   static constexpr size_t off_tw = off_x + x_bytes;
+   static constexpr size_t off_bar = off_tw + tw_bytes;
+   static constexpr size_t smem_bytes = off_bar + 16;
+};
+
+// ---- the kernel -------------------------------------------------------------------------------------
+template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL, int MINB>
+__global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid_constant__ FftArgs2 g2, const __grid_constant__ TmapPack tm)
+{
+   using T2 = typename Vec2<T>::type;
+   using G = Geom2<T, P, TX, LY, PADK, MODE, INL>;
+   static_assert(PlanInfo<P>::npass >= 2, "v2 kernels need at least one exchange");
+   static_assert(G::late_fits, "the late half of a tile must fit in the exchange buffer of its sub-tile");
+   static_assert(MODE == MODE_C2C || INL == IN_TILE || TX % 2 == 0, "real line pairs must land in the same zone");
+   constexpr int SP = TX;
+   constexpr int N = P::N, E = P::E, TPL = P::T, NH = N / 2 + 1;
+   extern __shared__ __align__(128) unsigned char smem2_raw[];
+   unsigned char *smem_raw = smem2_raw;
+   const FftArgs &g = g2.a;
+
+   unsigned char *Lbase = smem_raw;
+   unsigned char *Xbase = smem_raw + G::off_x;
+   T2 *tws = reinterpret_cast<T2 *>(smem_raw + G::off_tw);
+   unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + G::off_bar); // [0] early, [1] late
+
+   const int tid = threadIdx.x;
+   const int tx = tid % TX;
+   const int j = (tid / TX) % TPL;
+   const int ly = tid / (TX * TPL);
+   const int tiles_a = (g.na + TX - 1) / TX;
+   const long long ntiles = (long long)tiles_a * g.nb;
+   const long long ngroups = (ntiles + LY - 1) / LY;
+   T2 *lsm = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub) + tx;
+   const unsigned char *Lmine = Lbase + (size_t)ly * G::l_sub;
+   const unsigned char *Xmine = Xbase + (size_t)ly * G::x_sub + G::late_skew;
+
+   {
+      const T2 *__restrict__ twg = reinterpret_cast<const T2 *>(g.tw);
+      for (int i = tid; i < PlanInfo2<P>::tw_total; i += TX * LY * TPL) tws[i] = ldg_nc(twg + i);
+   }
+   if (tid == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      fence_mbar_init();
+   }
+   __syncthreads();
+   const unsigned conj_mask = g.backward ? 0x80000000u : 0u;
+   const bool noload = (g.debug & 2) != 0;
+
+   // ---- issue the loads of one half (which = 0 early / 1 late) of tile group `grp`; warp 0 only ------
+   auto issue = [&](long long grp, int which) {
+      if (noload) return;
+      void *mb = &bar[which];
+      if constexpr (INL == IN_TILE) {
+         if (tid == 0) {
+            unsigned total = 0;
+            for (int l = 0; l < LY; l++)
+               if (grp * LY + l < ntiles) total += (unsigned)(which ? g2.bytes_late : g2.bytes_early);
+            mbar_expect_tx(mb, total);
+            for (int l = 0; l < LY; l++) {
+               const long long tile = grp * LY + l;
+               if (tile >= ntiles) break;
+               const int b = (int)(tile / tiles_a);
+               const int a0 = (int)(tile - (long long)b * tiles_a) * TX;
+               unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
+               for (int i = 0; i < g2.nops; i++) {
+                  const LoadOp &op = g2.ops[i];
+                  if ((op.late & 1) != which) continue;
+                  unsigned char *dst = zone + (size_t)op.dst_row * G::row_bytes;
+                  if (op.late & 2) tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, b, op.c1, mb); // tensor dims ordered (a, b, e)
+                  else tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, op.c1, b, mb);
+               }
+            }
+         }
+      } else {
+         if (tid < 32) {
+            // one bulk copy per (line, piece); lines [l0, l1) of each sub-tile belong to this half
+            constexpr int l0c = 0, nE = G::lines_early, nL = G::nlines - G::lines_early;
+            const int nl = which ? nL : nE;
+            const int lbase = which ? nE : l0c;
+            const int np = (MODE == MODE_R2C) ? 1 : g.in.np;
+            // bytes: every valid line brings line_elems elements
+            unsigned total = 0;
+            for (int l = 0; l < LY; l++) {
+               const long long tile = grp * LY + l;
+               if (tile >= ntiles) break;
+               const int b = (int)(tile / tiles_a);
+               const long long a0 = (tile - (long long)b * tiles_a) * TX;
+               for (int q = 0; q < nl; q++) {
+                  const int line = lbase + q; // line index inside the sub-tile
+                  long long aline;            // index along the batch axis a, in lines of the INPUT array
+                  bool ok;
+                  if constexpr (MODE == MODE_C2C) { aline = a0 + line; ok = aline < g.na; }
+                  else { aline = 2 * a0 + line; ok = aline < g.na_real; }
+                  if (ok) total += (unsigned)(G::line_elems * G::line_esize);
+               }
+            }
+            if (tid == 0) mbar_expect_tx(mb, total);
+            __syncwarp();
+            const int nop = LY * nl * np;
+            for (int i = tid; i < nop; i += 32) {
+               const int m = i % np;
+               const int q = (i / np) % nl;
+               const int l = i / (np * nl);
+               const long long tile = grp * LY + l;
+               if (tile >= ntiles) continue;
+               const int b = (int)(tile / tiles_a);
+               const long long a0 = (tile - (long long)b * tiles_a) * TX;
+               const int line = lbase + q;
+               unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
+               unsigned char *dst = zone + (size_t)q * G::line_pitch;
+               if constexpr (MODE == MODE_R2C) {
+                  const long long aline = 2 * a0 + line;
+                  if (aline >= g.na_real) continue;
+                  const T *src = reinterpret_cast<const T *>(g.rptr) + aline * g.rsa + (long long)b * g.rsb;
+                  bulk_load(dst, src, (unsigned)(N * sizeof(T)), mb);
+               } else {
+                  const long long aline = (MODE == MODE_C2C) ? a0 + line : 2 * a0 + line;
+                  if (aline >= ((MODE == MODE_C2C) ? (long long)g.na : (long long)g.na_real)) continue;
+                  const int e0 = g.in.e0[m], e1 = g.in.e0[m + 1];
+                  const T2 *src = reinterpret_cast<const T2 *>(g.in.ptr[m]) + aline * g.in.sa[m] + (long long)b * g.in.sb[m];
+                  bulk_load(dst + (size_t)e0 * sizeof(T2), src, (unsigned)((e1 - e0) * sizeof(T2)), mb);
+               }
+            }
+         }
+      }
+   };
+
+   long long grp = blockIdx.x;
+   if (grp < ngroups) {
+      issue(grp, 0);
+      issue(grp, 1);
+   }
+   unsigned phase = 0;
+   for (; grp < ngroups; grp += gridDim.x, phase ^= 1) {
+      T2 v[E];
+      const long long tile = grp * LY + ly;
+      const bool in_range = tile < ntiles;
+      const long long b = tile / tiles_a;
+      const long long a = (tile - b * tiles_a) * TX + tx;
+      const bool valid = in_range && a < g.na;
+      const bool v1 = valid && (2 * a + 1 < g.na_real);
+      const long long nxt = grp + gridDim.x;
+
+      // ------------------------------------------------------------------ landing -> registers
+      if (!noload) {
+         mbar_wait(&bar[0], phase);
+         mbar_wait(&bar[1], phase);
+      }
+      if constexpr (MODE == MODE_C2C || MODE == MODE_R2C) {
+#pragma unroll
+         for (int s = 0; s < E; s++) {
+            const int row = j + TPL * s;
+            T2 x;
+            if constexpr (INL == IN_TILE) {
+               const unsigned char *src = (row < G::rows_early) ? Lmine + (size_t)row * G::row_bytes : Xmine + (size_t)(row - G::rows_early) * G::row_bytes;
+               x = reinterpret_cast<const T2 *>(src)[tx];
+            } else if constexpr (MODE == MODE_C2C) {
+               const unsigned char *line = (tx < G::lines_early) ? Lmine + (size_t)tx * G::line_pitch : Xmine + (size_t)(tx - G::lines_early) * G::line_pitch;
+               x = reinterpret_cast<const T2 *>(line)[row];
+            } else { // R2C from two real lines
+               const int l0 = 2 * tx;
+               const unsigned char *la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+               x.x = reinterpret_cast<const T *>(la)[row];
+               x.y = reinterpret_cast<const T *>(la + G::line_pitch)[row];
+            }
+            if constexpr (MODE == MODE_C2C) x.y = flip_sign(x.y, conj_mask);
+            else if (!v1) x.y = 0;
+            if (!valid) x = T2{0, 0};
+            v[s] = x;
+         }
+      } else { // C2R: Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]); the forward passes get conj(Z)
+#pragma unroll
+         for (int s = 0; s < E; s++) {
+            const int p = j + TPL * s;
+            const int k = (p <= N / 2) ? p : N - p;
+            T2 A, B;
+            if constexpr (INL == IN_TILE) {
+               const unsigned char *src = (k < G::rows_early) ? Lmine + (size_t)k * G::row_bytes : Xmine + (size_t)(k - G::rows_early) * G::row_bytes;
+               A = reinterpret_cast<const T2 *>(src)[2 * tx];
+               B = reinterpret_cast<const T2 *>(src)[2 * tx + 1];
+            } else {
+               const int l0 = 2 * tx;
+               const unsigned char *la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+               A = reinterpret_cast<const T2 *>(la)[k];
+               B = reinterpret_cast<const T2 *>(la + G::line_pitch)[k];
+            }
+            if (!valid) A = T2{0, 0};
+            if (!v1) B = T2{0, 0};
+            if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
+            v[s] = (p <= N / 2) ? T2{A.x - B.y, -(A.y + B.x)} : T2{A.x + B.y, A.y - B.x};
+         }
+      }
+      __syncthreads(); // everybody holds its tile: L (and the late zone, until the first scatter) are free
+      if (nxt < ngroups) issue(nxt, 0);
+
+      auto late = [&]() {
+         fence_proxy_async(); // generic-proxy writes to X (scatters) before the async-proxy writes of the next landing
+         __syncthreads(); // the whole block is done with the exchange buffer
+         if (nxt < ngroups) issue(nxt, 1);
+      };
+
+      // ------------------------------------------------------------------ transform
+      bool late_done = false;
+      if (!g.passthrough) {
+         if constexpr (MODE == MODE_R2C) {
+            auto nolate = [&]() {};
+            RunPasses2<T, P, 0, SP, PADK, decltype(nolate)>::run(v, j, lsm, tws, nolate);
+         } else {
+            RunPasses2<T, P, 0, SP, PADK, decltype(late)>::run(v, j, lsm, tws, late);
+            late_done = true;
+         }
+      }
+
+      // ------------------------------------------------------------------ store
+      if constexpr (MODE == MODE_C2C) {
+         if (!late_done) late();
+         if (valid && !(g.debug & 1)) {
+            if (g.out.np == 1) {
+               T2 *p = reinterpret_cast<T2 *>(g.out.ptr[0]) + (long long)j * g.out.se[0] + a * g.out.sa[0] + b * g.out.sb[0];
+               const long long step = (long long)TPL * g.out.se[0];
+#pragma unroll
+               for (int s = 0; s < E; s++) {
+                  T2 x = v[s];
+                  x.y = flip_sign(x.y, conj_mask);
+                  p[s * step] = x;
+               }
+            } else {
+#pragma unroll
+               for (int s = 0; s < E; s++) {
+                  T2 x = v[s];
+                  x.y = flip_sign(x.y, conj_mask);
+                  store_piece<T2>(g.out, j + TPL * s, a, b, x);
+               }
+            }
+         }
+      } else if constexpr (MODE == MODE_C2R) {
+         if (!late_done) late();
+         T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
+         const bool pairvec = (g.rsa == 1) && ((g.rsb & 1) == 0) && ((g.rse & 1) == 0) && ((reinterpret_cast<uintptr_t>(rp) % (2 * sizeof(T))) == 0);
+         if (!(g.debug & 1)) {
+#pragma unroll
+            for (int s = 0; s < E; s++) {
+               const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
+               if (pairvec && v1) {
+                  *reinterpret_cast<T2 *>(rp + off) = T2{v[s].x, -v[s].y};
+               } else {
+                  if (valid) rp[off] = v[s].x;
+                  if (v1) rp[off + g.rsa] = -v[s].y;
+               }
+            }
+         }
+      } else { // R2C: separate the two spectra through the exchange buffer, then free it
+         __syncthreads();
+#pragma unroll
+         for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * SP] = v[s];
+         __syncthreads();
+         T2 zn[E / 2 + 1];
+#pragma unroll
+         for (int s = 0; s <= E / 2; s++) {
+            const int k = j + TPL * s;
+            zn[s] = T2{0, 0};
+            if (k <= N / 2 && (s < E / 2 || j == 0)) zn[s] = lsm[padix<PADK>((N - k) % N) * SP];
+         }
+         late();
+         if (!(g.debug & 1)) {
+#pragma unroll
+            for (int s = 0; s <= E / 2; s++) {
+               const int k = j + TPL * s;
+               if (k <= N / 2 && (s < E / 2 || j == 0)) {
+                  const T2 zk = v[s];
+                  const T hf = (T)0.5;
+                  T2 A = T2{(zk.x + zn[s].x) * hf, (zk.y - zn[s].y) * hf};
+                  T2 B = T2{(zk.y + zn[s].y) * hf, (zn[s].x - zk.x) * hf};
+                  if (valid) store_piece<T2>(g.out, k, 2 * a, b, A);
+                  if (v1) store_piece<T2>(g.out, k, 2 * a + 1, b, B);
+               }
+            }
+         }
+      }
+   }
+}
+
+} // namespace d2d

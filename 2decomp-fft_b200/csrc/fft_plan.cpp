@@ -14,6 +14,8 @@
 
 namespace d2d {
 
+bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_t *err);
+
 struct Plan {
    Ctx *ctx;
    int format, nx, ny, nz, f64, inplace;
@@ -89,7 +91,8 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    snprintf(label, sizeof(label), "fft_%s_%c%s", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil],
             (mode == MODE_C2C && chain) ? (backward ? "_bwd" : "_fwd") : "");
    ProfScope ps(ctx, label, bytes);
-   cudaError_t e = k->launch(g, ctx->stream);
+   cudaError_t e = cudaSuccess;
+   if (!fft_v2_try_launch(ctx, g, f64, mode, &e)) e = k->launch(g, ctx->stream);
    if (e != cudaSuccess) throw Error(1000 + (int)e, std::string("FFT kernel launch failed: ") + cudaGetErrorString(e));
    ctx->launches++;
 }

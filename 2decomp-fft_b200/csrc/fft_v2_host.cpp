@@ -1,0 +1,198 @@
+// fft_v2_host.cpp -- host side of the TMA-staged FFT kernels (fft_kernel_v2.cuh): decides whether a
+// stage can run on them (alignment rules of the TMA engine), builds the tensor maps and the list of
+// box loads of a tile, and launches.  Falls back (returns false) to the v1 kernels otherwise.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "fft_registry.h"
+
+namespace d2d {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+   static EncodeTiledFn fn = []() -> EncodeTiledFn {
+      void *p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+         return nullptr;
+      return (EncodeTiledFn)p;
+   }();
+   return fn;
+}
+
+int env_int(const char *name, int dflt)
+{
+   const char *v = getenv(name);
+   return v ? atoi(v) : dflt;
+}
+
+bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// One piece of a tile-like input seen as a 3-D tensor (dim0 = batch axis a in scalars, then the
+// transform axis e and the batch axis b ordered by increasing stride).
+struct PieceDesc {
+   void *base;
+   long long n0;         // extent of dim 0 in scalars
+   long long rows;       // extent along e
+   long long stride_e, stride_b; // bytes
+   long long nb;
+};
+
+struct Builder {
+   TmapPack tm;
+   int nmaps = 0;
+   struct Key { int piece, box_rows; } keys[kMaxTmaps];
+   int swap[kMaxTmaps];
+   int find_or_make(int piece, int box_rows, const PieceDesc &d, int f64, int box0)
+   {
+      for (int i = 0; i < nmaps; i++)
+         if (keys[i].piece == piece && keys[i].box_rows == box_rows) return i;
+      if (nmaps == kMaxTmaps) return -1;
+      EncodeTiledFn fn = encode_fn();
+      if (!fn) return -1;
+      const int es = f64 ? 8 : 4;
+      // outer dims sorted by stride (the engine wants non-decreasing strides to be safe)
+      const long long sb = d.nb > 1 ? d.stride_b : 0;
+      const bool sw = d.nb > 1 && sb < d.stride_e; // b before e
+      cuuint64_t dims[3], strides[2];
+      cuuint32_t box[3], estr[3] = {1, 1, 1};
+      dims[0] = (cuuint64_t)d.n0;
+      box[0] = (cuuint32_t)box0;
+      const long long nb_stride = d.nb > 1 ? sb : (d.stride_e * d.rows + 15) / 16 * 16; // any legal value for an extent-1 axis
+      if (!sw) {
+         dims[1] = (cuuint64_t)d.rows; strides[0] = (cuuint64_t)d.stride_e; box[1] = (cuuint32_t)box_rows;
+         dims[2] = (cuuint64_t)d.nb;   strides[1] = (cuuint64_t)nb_stride;  box[2] = 1;
+      } else {
+         dims[1] = (cuuint64_t)d.nb;   strides[0] = (cuuint64_t)sb;         box[1] = 1;
+         dims[2] = (cuuint64_t)d.rows; strides[1] = (cuuint64_t)d.stride_e; box[2] = (cuuint32_t)box_rows;
+      }
+      static const int promo = env_int("D2D_TMA_L2PROMO", 1);
+      const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                        : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                     : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      CUresult r = fn(&tm.m[nmaps], es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.base, dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return -1;
+      keys[nmaps] = {piece, box_rows};
+      swap[nmaps] = sw ? 1 : 0;
+      return nmaps++;
+   }
+};
+
+bool stride_ok(long long bytes) { return bytes > 0 && (bytes & 15) == 0 && bytes < (1LL << 40); }
+
+} // namespace
+
+// returns true when the stage was launched on a v2 kernel
+bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_t *err)
+{
+   static const int enabled = env_int("D2D_V2", 1);
+   *err = cudaSuccess;
+   if (!enabled || g.passthrough) return false;
+   const int es = f64 ? 8 : 4; // scalar size
+   const int ces = 2 * es;     // complex size
+   // ---- which input layout? ----------------------------------------------------------------------
+   int inl = -1;
+   if (mode == MODE_R2C) {
+      if (g.rsa == 1) inl = IN_TILE;
+      else if (g.rse == 1) inl = IN_LINE;
+   } else {
+      bool tile = true, line = true;
+      for (int m = 0; m < g.in.np; m++) {
+         tile = tile && g.in.sa[m] == 1;
+         line = line && g.in.se[m] == 1;
+      }
+      inl = tile ? IN_TILE : line ? IN_LINE : -1;
+      if (tile && line) inl = (g.na > 1) ? IN_TILE : IN_LINE;
+   }
+   if (inl < 0) return false;
+   const FftKernelInfo *k = fft_find_v2(g.n, f64, mode, inl);
+   if (!k) return false;
+   if (g.nb > 65535 * 32767LL) return false;
+
+   FftArgs2 a2{};
+   a2.a = g;
+   a2.a.tw = twiddles_for(ctx->device, g.n, f64, 1);
+   Builder B;
+   memset(&B.tm, 0, sizeof(B.tm));
+   const int N = g.n, NH = N / 2 + 1;
+
+   if (inl == IN_LINE) {
+      if (mode == MODE_R2C) {
+         if (!aligned16(g.rptr) || ((g.rsa * es) & 15) || ((g.rsb * es) & 15) || (((long long)N * es) & 15)) return false;
+      } else {
+         const int len_total = (mode == MODE_C2R) ? NH : N;
+         if (g.in.e0[g.in.np] != len_total) return false;
+         for (int m = 0; m < g.in.np; m++) {
+            if (!aligned16(g.in.ptr[m]) || ((g.in.sa[m] * ces) & 15) || ((g.in.sb[m] * ces) & 15)) return false;
+            if (((long long)g.in.e0[m] * ces) & 15) return false;
+            if (((long long)(g.in.e0[m + 1] - g.in.e0[m]) * ces) & 15) return false;
+         }
+      }
+   } else {
+      // ---- tile-like: tensor maps + box list ----------------------------------------------------------
+      const int np = (mode == MODE_R2C) ? 1 : g.in.np;
+      const int rows_total = (mode == MODE_C2R) ? NH : N;
+      const int box0 = k->row_bytes / es; // scalars per landing row
+      a2.c0_mul = box0 / k->tx;
+      int row = 0; // global row (along e) of the tile
+      a2.nops = 0;
+      for (int m = 0; m < np; m++) {
+         PieceDesc d{};
+         int len;
+         if (mode == MODE_R2C) {
+            d.base = g.rptr;
+            d.n0 = g.na_real;
+            len = N;
+            d.stride_e = g.rse * (long long)es;
+            d.stride_b = g.rsb * (long long)es;
+         } else {
+            d.base = g.in.ptr[m];
+            d.n0 = (mode == MODE_C2R) ? 2LL * g.na_real : 2LL * g.na;
+            len = g.in.e0[m + 1] - g.in.e0[m];
+            if (g.in.e0[m] != row) return false;
+            d.stride_e = g.in.se[m] * (long long)ces;
+            d.stride_b = g.in.sb[m] * (long long)ces;
+         }
+         d.rows = len;
+         d.nb = g.nb;
+         if (!aligned16(d.base) || !stride_ok(d.stride_e) || (d.nb > 1 && !stride_ok(d.stride_b))) return false;
+         if (d.n0 >= (1LL << 32) || d.rows >= (1LL << 32)) return false;
+         // cut [row, row+len) at the early/late boundary, then into power-of-two boxes of <= 256 rows
+         int done = 0;
+         while (done < len) {
+            const int grow = row + done;
+            const int late = grow >= k->rows_early;
+            int room = late ? (rows_total - grow) : (k->rows_early - grow);
+            room = std::min(room, len - done);
+            int br = 256;
+            while (br > room) br >>= 1;
+            const int mi = B.find_or_make(m, br, d, f64, box0);
+            if (mi < 0 || a2.nops == kMaxLoadOps) return false;
+            LoadOp &op = a2.ops[a2.nops++];
+            op.map = (short)mi;
+            op.late = (short)(late | (B.swap[mi] << 1));
+            op.c1 = done;
+            op.dst_row = late ? grow - k->rows_early : grow;
+            op.bytes = br * k->row_bytes;
+            (late ? a2.bytes_late : a2.bytes_early) += op.bytes;
+            done += br;
+         }
+         row += len;
+      }
+      if (row != rows_total) return false;
+   }
+   *err = k->launch2(a2, B.tm, ctx->stream);
+   return true;
+}
+
+} // namespace d2d
