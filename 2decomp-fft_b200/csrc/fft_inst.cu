@@ -85,11 +85,12 @@ template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
 };
 
 // ---- v2: TMA-staged kernels (fft_kernel_v2.cuh) --------------------------------------------------
-constexpr int TX2 = 64 / (int)sizeof(T2);                                  // 64-byte tile rows
-constexpr int LY2 = cmax(1, kTargetThreads / (TX2 * P::T));
+constexpr int TX2N = 64 / (int)sizeof(T2);                                 // 64-byte tile rows, two blocks per SM
+constexpr int TX2W = 128 / (int)sizeof(T2);                                // 128-byte tile rows (one L2 line per row)
 constexpr size_t kSmemSM = 227 * 1024;
 
-template <int MODE, int INL> struct Inst2 {
+template <int MODE, int INL, int TX2> struct Inst2 {
+   static constexpr int LY2 = cmax(1, kTargetThreads / (TX2 * P::T));
    using G = Geom2<real_t, P, TX2, LY2, PADK, MODE, INL>;
    static constexpr bool fits = PlanInfo<P>::npass >= 2 && P::N >= 256 && G::late_fits && G::threads <= 1024 && G::smem_bytes + 1024 <= kSmemSM;
    static constexpr int MINB = (G::threads <= 256 && 2 * (G::smem_bytes + 1024) <= kSmemSM) ? 2 : 1;
@@ -142,12 +143,18 @@ template <int MODE, int INL> struct Inst2 {
 struct Registrar {
    Registrar()
    {
-      Inst2<MODE_C2C, IN_TILE>::reg();
-      Inst2<MODE_C2C, IN_LINE>::reg();
-      Inst2<MODE_R2C, IN_TILE>::reg();
-      Inst2<MODE_R2C, IN_LINE>::reg();
-      Inst2<MODE_C2R, IN_TILE>::reg();
-      Inst2<MODE_C2R, IN_LINE>::reg();
+      Inst2<MODE_C2C, IN_TILE, TX2N>::reg();
+      Inst2<MODE_C2C, IN_LINE, TX2N>::reg();
+      Inst2<MODE_R2C, IN_TILE, TX2N>::reg();
+      Inst2<MODE_R2C, IN_LINE, TX2N>::reg();
+      Inst2<MODE_C2R, IN_TILE, TX2N>::reg();
+      Inst2<MODE_C2R, IN_LINE, TX2N>::reg();
+      Inst2<MODE_C2C, IN_TILE, TX2W>::reg();
+      Inst2<MODE_C2C, IN_LINE, TX2W>::reg();
+      Inst2<MODE_R2C, IN_TILE, TX2W>::reg();
+      Inst2<MODE_R2C, IN_LINE, TX2W>::reg();
+      Inst2<MODE_C2R, IN_TILE, TX2W>::reg();
+      Inst2<MODE_C2R, IN_LINE, TX2W>::reg();
       Inst<1, LY_LINE, MODE_C2C, false>::reg(KIND_LINE);
       Inst<1, LY_LINE, MODE_R2C, false>::reg(KIND_LINE);
       Inst<1, LY_LINE, MODE_C2R, false>::reg(KIND_LINE);

@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    const int j = (tid / TX) % TPL;
    const int ly = tid / (TX * TPL);
    const int tiles_a = (g.na + TX - 1) / TX;
-   const long long ntiles = (long long)tiles_a * g.nb;
-   const long long ngroups = (ntiles + LY - 1) / LY;
+   const int ntiles = tiles_a * g.nb; // the host guarantees < 2^31
+   const int ngroups = (ntiles + LY - 1) / LY;
    T2 *lsm = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub) + tx;
    const unsigned char *Lmine = Lbase + (size_t)ly * G::l_sub;
    const unsigned char *Xmine = Xbase + (size_t)ly * G::x_sub + G::late_skew;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    const bool noload = (g.debug & 2) != 0;
 
    // ---- issue the loads of one half (which = 0 early / 1 late) of tile group `grp`; warp 0 only ------
-   auto issue = [&](long long grp, int which) {
+   auto issue = [&](int grp, int which) {
       if (noload) return;
       void *mb = &bar[which];
       if constexpr (INL == IN_TILE) {
@@ -255,10 +255,10 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                if (grp * LY + l < ntiles) total += (unsigned)(which ? g2.bytes_late : g2.bytes_early);
             mbar_expect_tx(mb, total);
             for (int l = 0; l < LY; l++) {
-               const long long tile = grp * LY + l;
+               const int tile = grp * LY + l;
                if (tile >= ntiles) break;
-               const int b = (int)(tile / tiles_a);
-               const int a0 = (int)(tile - (long long)b * tiles_a) * TX;
+               const int b = tile / tiles_a;
+               const int a0 = (tile - b * tiles_a) * TX;
                unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
                for (int i = 0; i < g2.nops; i++) {
                   const LoadOp &op = g2.ops[i];
@@ -271,51 +271,42 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          }
       } else {
          if (tid < 32) {
-            // one bulk copy per (line, piece); lines [l0, l1) of each sub-tile belong to this half
-            constexpr int l0c = 0, nE = G::lines_early, nL = G::nlines - G::lines_early;
+            // one bulk copy per (line, piece); lines [lbase, lbase + nl) of each sub-tile belong to this half
+            constexpr int nE = G::lines_early, nL = G::nlines - G::lines_early;
             const int nl = which ? nL : nE;
-            const int lbase = which ? nE : l0c;
+            const int lbase = which ? nE : 0;
             const int np = (MODE == MODE_R2C) ? 1 : g.in.np;
-            // bytes: every valid line brings line_elems elements
-            unsigned total = 0;
-            for (int l = 0; l < LY; l++) {
-               const long long tile = grp * LY + l;
-               if (tile >= ntiles) break;
-               const int b = (int)(tile / tiles_a);
-               const long long a0 = (tile - (long long)b * tiles_a) * TX;
-               for (int q = 0; q < nl; q++) {
-                  const int line = lbase + q; // line index inside the sub-tile
-                  long long aline;            // index along the batch axis a, in lines of the INPUT array
-                  bool ok;
-                  if constexpr (MODE == MODE_C2C) { aline = a0 + line; ok = aline < g.na; }
-                  else { aline = 2 * a0 + line; ok = aline < g.na_real; }
-                  if (ok) total += (unsigned)(G::line_elems * G::line_esize);
+            const int limit = (MODE == MODE_C2C) ? g.na : g.na_real; // input lines along a
+            constexpr int lmul = (MODE == MODE_C2C) ? 1 : 2;          // input lines per complex line of the tile
+            if (tid == 0) {
+               unsigned lines = 0;
+               for (int l = 0; l < LY; l++) {
+                  const int tile = grp * LY + l;
+                  if (tile >= ntiles) break;
+                  const int first = lmul * ((tile % tiles_a) * TX) + lbase;
+                  const int cnt = limit - first;
+                  lines += (unsigned)(cnt < 0 ? 0 : cnt > nl ? nl : cnt);
                }
+               mbar_expect_tx(mb, lines * (unsigned)(G::line_elems * G::line_esize));
             }
-            if (tid == 0) mbar_expect_tx(mb, total);
             __syncwarp();
             const int nop = LY * nl * np;
             for (int i = tid; i < nop; i += 32) {
                const int m = i % np;
                const int q = (i / np) % nl;
                const int l = i / (np * nl);
-               const long long tile = grp * LY + l;
+               const int tile = grp * LY + l;
                if (tile >= ntiles) continue;
-               const int b = (int)(tile / tiles_a);
-               const long long a0 = (tile - (long long)b * tiles_a) * TX;
-               const int line = lbase + q;
-               unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
-               unsigned char *dst = zone + (size_t)q * G::line_pitch;
+               const int b = tile / tiles_a;
+               const int aline = lmul * ((tile - b * tiles_a) * TX) + lbase + q;
+               if (aline >= limit) continue;
+               unsigned char *dst = (which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub)) + (size_t)q * G::line_pitch;
                if constexpr (MODE == MODE_R2C) {
-                  const long long aline = 2 * a0 + line;
-                  if (aline >= g.na_real) continue;
-                  const T *src = reinterpret_cast<const T *>(g.rptr) + aline * g.rsa + (long long)b * g.rsb;
+                  const T *src = reinterpret_cast<const T *>(g.rptr) + (long long)aline * g.rsa + (long long)b * g.rsb;
                   bulk_load(dst, src, (unsigned)(N * sizeof(T)), mb);
                } else {
-                  const long long aline = (MODE == MODE_C2C) ? a0 + line : 2 * a0 + line;
-                  if (aline >= ((MODE == MODE_C2C) ? (long long)g.na : (long long)g.na_real)) continue;
                   const int e0 = g.in.e0[m], e1 = g.in.e0[m + 1];
-                  const T2 *src = reinterpret_cast<const T2 *>(g.in.ptr[m]) + aline * g.in.sa[m] + (long long)b * g.in.sb[m];
+                  const T2 *src = reinterpret_cast<const T2 *>(g.in.ptr[m]) + (long long)aline * g.in.sa[m] + (long long)b * g.in.sb[m];
                   bulk_load(dst + (size_t)e0 * sizeof(T2), src, (unsigned)((e1 - e0) * sizeof(T2)), mb);
                }
             }
@@ -323,7 +314,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
       }
    };
 
-   long long grp = blockIdx.x;
+   int grp = blockIdx.x;
    if (grp < ngroups) {
       issue(grp, 0);
       issue(grp, 1);
@@ -331,13 +322,13 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    unsigned phase = 0;
    for (; grp < ngroups; grp += gridDim.x, phase ^= 1) {
       T2 v[E];
-      const long long tile = grp * LY + ly;
+      const int tile = grp * LY + ly;
       const bool in_range = tile < ntiles;
-      const long long b = tile / tiles_a;
-      const long long a = (tile - b * tiles_a) * TX + tx;
+      const int b = tile / tiles_a;
+      const int a = (tile - b * tiles_a) * TX + tx;
       const bool valid = in_range && a < g.na;
       const bool v1 = valid && (2 * a + 1 < g.na_real);
-      const long long nxt = grp + gridDim.x;
+      const int nxt = grp + (int)gridDim.x;
 
       // ------------------------------------------------------------------ landing -> registers
       if (!noload) {
@@ -367,25 +358,31 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             v[s] = x;
          }
       } else { // C2R: Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]); the forward passes get conj(Z)
+         const unsigned char *la = nullptr;
+         if constexpr (INL == IN_LINE) {
+            const int l0 = 2 * tx;
+            la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+         }
 #pragma unroll
          for (int s = 0; s < E; s++) {
             const int p = j + TPL * s;
-            const int k = (p <= N / 2) ? p : N - p;
+            // positions of slot s span [TPL s, TPL s + TPL): entirely below / above n/2 except for one slot
+            const bool lower = (TPL * s + TPL - 1 <= N / 2) ? true : (TPL * s > N / 2) ? false : (p <= N / 2);
+            const int k = lower ? p : N - p;
             T2 A, B;
             if constexpr (INL == IN_TILE) {
                const unsigned char *src = (k < G::rows_early) ? Lmine + (size_t)k * G::row_bytes : Xmine + (size_t)(k - G::rows_early) * G::row_bytes;
                A = reinterpret_cast<const T2 *>(src)[2 * tx];
                B = reinterpret_cast<const T2 *>(src)[2 * tx + 1];
             } else {
-               const int l0 = 2 * tx;
-               const unsigned char *la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
                A = reinterpret_cast<const T2 *>(la)[k];
                B = reinterpret_cast<const T2 *>(la + G::line_pitch)[k];
             }
-            if (!valid) A = T2{0, 0};
             if (!v1) B = T2{0, 0};
-            if (k == 0 || 2 * k == N) { A.y = 0; B.y = 0; }
-            v[s] = (p <= N / 2) ? T2{A.x - B.y, -(A.y + B.x)} : T2{A.x + B.y, A.y - B.x};
+            if (TPL * s == 0 || TPL * s == N / 2) { // only these slots can hold bin 0 / bin n/2 (thread j = 0)
+               if (j == 0) { A.y = 0; B.y = 0; }
+            }
+            v[s] = lower ? T2{A.x - B.y, -(A.y + B.x)} : T2{A.x + B.y, A.y - B.x};
          }
       }
       __syncthreads(); // everybody holds its tile: L (and the late zone, until the first scatter) are free
@@ -414,13 +411,14 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          if (!late_done) late();
          if (valid && !(g.debug & 1)) {
             if (g.out.np == 1) {
-               T2 *p = reinterpret_cast<T2 *>(g.out.ptr[0]) + (long long)j * g.out.se[0] + a * g.out.sa[0] + b * g.out.sb[0];
+               T2 *p = reinterpret_cast<T2 *>(g.out.ptr[0]) + (long long)j * g.out.se[0] + (long long)a * g.out.sa[0] + (long long)b * g.out.sb[0];
                const long long step = (long long)TPL * g.out.se[0];
 #pragma unroll
                for (int s = 0; s < E; s++) {
                   T2 x = v[s];
                   x.y = flip_sign(x.y, conj_mask);
-                  p[s * step] = x;
+                  *p = x;
+                  p += step;
                }
             } else {
 #pragma unroll
@@ -433,17 +431,23 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          }
       } else if constexpr (MODE == MODE_C2R) {
          if (!late_done) late();
-         T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
-         const bool pairvec = (g.rsa == 1) && ((g.rsb & 1) == 0) && ((g.rse & 1) == 0) && ((reinterpret_cast<uintptr_t>(rp) % (2 * sizeof(T))) == 0);
+         // real output: element e of real line ar at rptr + e rse + ar rsa + b rsb; lines 2a, 2a+1 of this thread
+         T *__restrict__ rp = reinterpret_cast<T *>(g.rptr) + (long long)j * g.rse + (long long)(2 * a) * g.rsa + (long long)b * g.rsb;
+         const long long step = (long long)TPL * g.rse;
+         const bool pairvec = (g.rsa == 1) && ((g.rsb & 1) == 0) && ((g.rse & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.rptr) % (2 * sizeof(T))) == 0);
          if (!(g.debug & 1)) {
+            if (pairvec && v1) {
 #pragma unroll
-            for (int s = 0; s < E; s++) {
-               const long long off = (long long)(j + TPL * s) * g.rse + (2 * a) * g.rsa + b * g.rsb;
-               if (pairvec && v1) {
-                  *reinterpret_cast<T2 *>(rp + off) = T2{v[s].x, -v[s].y};
-               } else {
-                  if (valid) rp[off] = v[s].x;
-                  if (v1) rp[off + g.rsa] = -v[s].y;
+               for (int s = 0; s < E; s++) {
+                  *reinterpret_cast<T2 *>(rp) = T2{v[s].x, -v[s].y};
+                  rp += step;
+               }
+            } else if (valid) {
+#pragma unroll
+               for (int s = 0; s < E; s++) {
+                  rp[0] = v[s].x;
+                  if (v1) rp[g.rsa] = -v[s].y;
+                  rp += step;
                }
             }
          }

@@ -26,7 +26,7 @@ struct FftKernelInfo {
 void fft_register(const FftKernelInfo &);
 // exact lookup; nullptr if this (n, dtype, kind, mode, pairvec) was not compiled
 const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, int line_in = 0);
-const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl);
+const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl, int row_bytes = 64);
 int fft_registry_size();
 const FftKernelInfo *fft_registry_at(int i);
 

@@ -115,9 +115,18 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       if (tile && line) inl = (g.na > 1) ? IN_TILE : IN_LINE;
    }
    if (inl < 0) return false;
-   const FftKernelInfo *k = fft_find_v2(g.n, f64, mode, inl);
+   // tile-like OUTPUT (TX adjacent lines are contiguous on the store side)?  Scattered 64-byte stores cost the
+   // memory system far more than 128-byte ones (tools/micro/membench.cu), so those stages may use wide tiles.
+   bool tile_out;
+   if (mode == MODE_C2R) tile_out = g.rsa == 1 && g.rse != 1;
+   else tile_out = g.out.sa[0] == 1 && g.out.se[0] != 1;
+   static const int rb_all = env_int("D2D_V2_ROWBYTES", 64), rb_tout = env_int("D2D_V2_ROWBYTES_TILEOUT", 0);
+   // default: 128-byte rows for fp64 tile-out stages (one block of 512 threads per SM); fp32 would need 1024 threads
+   const int want = tile_out ? (rb_tout ? rb_tout : (f64 ? 128 : 64)) : rb_all;
+   const FftKernelInfo *k = fft_find_v2(g.n, f64, mode, inl, want);
+   if (!k) k = fft_find_v2(g.n, f64, mode, inl, 64);
    if (!k) return false;
-   if (g.nb > 65535 * 32767LL) return false;
+   if ((long long)((g.na + 3) / 4) * g.nb >= (1LL << 31)) return false; // the kernels count tiles in 32 bits
 
    FftArgs2 a2{};
    a2.a = g;
