@@ -1,0 +1,2 @@
+export NCCL_DEBUG=WARN
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-e2e 2>&1 | tail -5
