@@ -58,6 +58,12 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no fallback path)")
+        try:
+            # torch bundles a newer NCCL (libnccl.so.2, same soname as the system one this library links to):
+            # whichever is loaded first serves both, so let torch's superset win
+            import torch  # noqa: F401
+        except ImportError:
+            pass
         l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         l.d2d_last_error.restype = C.c_char_p
         l.d2d_version.restype = C.c_char_p

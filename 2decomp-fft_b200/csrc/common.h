@@ -38,6 +38,8 @@ const std::string &get_last_error();
    } while (0)
 
 constexpr int kMaxP = kMaxPieces; // max ranks along one side of the process grid
+constexpr int kMaxRanks = kMaxPieces * kMaxPieces;
+constexpr int kWorkBuffers = 3;
 
 // decomp_info (src/info.f90:19-47).  0-based starts internally; the C ABI converts to 1-based.
 struct Decomp {
@@ -73,6 +75,8 @@ struct Transport {
    // transport allows it.
    virtual void exchange(const std::vector<PeerXfer> &xf, cudaStream_t st) = 0;
    virtual void barrier(cudaStream_t st) = 0;
+   // all-gather of `bytes` host bytes per rank (blocking; bootstrap use only)
+   virtual void allgather(const void *send_host, void *recv_host, size_t bytes, cudaStream_t st) = 0;
 };
 
 Transport *make_nccl_transport(const unsigned char id[128], int nranks, int rank);
@@ -96,8 +100,9 @@ struct Ctx {
    bool blocking = true;
    int64_t launches = 0;
    // grow-only work buffers (the reference's work1/work2 high-water mark, src/decomp_2d.f90:461-485)
-   void *work[3] = {nullptr, nullptr, nullptr};
-   size_t work_bytes[3] = {0, 0, 0};
+   void *work[kWorkBuffers] = {nullptr, nullptr, nullptr};
+   size_t work_bytes[kWorkBuffers] = {0, 0, 0};
+   struct P2P *p2p = nullptr; // peer-mapped work buffers + flags (p2p.cpp); null when unused
    // profiling
    bool profiling = false;
    std::vector<ProfEntry> prof;
@@ -175,6 +180,17 @@ PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, v
 void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int padq);
 
 void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src, void *dst);
+
+// peer-memory path of the fused transforms (p2p.cpp)
+void p2p_publish(Ctx *ctx);
+void p2p_destroy(struct P2P *p);
+bool p2p_active(const Ctx *ctx);
+void p2p_invalidate(Ctx *ctx);
+void *p2p_peer_work(const Ctx *ctx, int w, int rank);
+size_t p2p_peer_bytes(const Ctx *ctx, int w, int rank);
+uint32_t p2p_next_epoch(Ctx *ctx);
+void p2p_signal(Ctx *ctx, int peer, int which, uint32_t epoch);
+void p2p_wait(Ctx *ctx, int peer, int which, uint32_t epoch);
 
 } // namespace d2d
 

@@ -101,6 +101,7 @@ void *Ctx::reserve(int which, size_t bytes)
 {
    if (bytes > work_bytes[which]) {
       D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+      p2p_invalidate(this); // peers hold mappings of the old buffer; the next plan creation publishes again
       if (work[which]) D2D_CHECK_CUDA(cudaFree(work[which]));
       work[which] = nullptr;
       work_bytes[which] = 0;
@@ -155,6 +156,8 @@ Ctx::~Ctx()
 {
    cudaSetDevice(device);
    if (stream) cudaStreamSynchronize(stream);
+   if (p2p) p2p_destroy(p2p);
+   p2p = nullptr;
    tr.reset();
    for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
    for (auto e : event_pool) cudaEventDestroy(e);
@@ -214,6 +217,7 @@ struct LocalTransport : Transport {
       D2D_CHECK_CUDA(cudaStreamSynchronize(st));
       g->barrier();
    }
+   void allgather(const void *, void *, size_t, cudaStream_t) override { D2D_REQUIRE(false, "allgather: not available on the in-process transport"); }
 };
 } // namespace
 Transport *make_local_transport(Group *g, int rank) { return new LocalTransport(g, rank); }

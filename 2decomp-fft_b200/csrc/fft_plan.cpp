@@ -108,12 +108,16 @@ struct StageDef {
 // both.  With a 1-rank communicator the exchange vanishes and the consumer reads the producer's
 // buffer.  Three work buffers rotate; a single-rank complex-output transform borrows `out` as the
 // first one.
+static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward);
+static size_t uniform_work_bytes(const Plan &p);
+
 static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
    Ctx *ctx = p.ctx;
+   if (p2p_active(ctx)) return run_chain_p2p(p, dc, dr, st, in, out, backward);
    const int es = p.f64 ? 16 : 8;
    const int padq = 128 / es;
-   const size_t wbytes = (size_t)es * fft_work_elems(dc, padq);
+   const size_t wbytes = uniform_work_bytes(p);
    // `out` can stand in for the first work buffer only when the padded wire layout fits in it
    const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C && wbytes <= (size_t)es * dc.pencil_elems(st[2].pencil);
    int live_a = -1, live_b = -1; // work buffers holding the current stage's input
@@ -157,15 +161,118 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
    }
 }
 
+// work-buffer size (bytes) that is the same on every rank of the grid (ragged decompositions give the last
+// ranks bigger pencils): peers address each other's buffers, so all of them must (re)allocate together
+static size_t uniform_work_bytes(const Plan &p)
+{
+   const int es = p.f64 ? 16 : 8;
+   int64_t m = 0;
+   for (int r = 0; r < p.ctx->nranks; r++) {
+      Decomp a, b;
+      decomp_init(a, p.sp.d.nx, p.sp.d.ny, p.sp.d.nz, p.ctx->p_row, p.ctx->p_col, r);
+      decomp_init(b, p.ph.d.nx, p.ph.d.ny, p.ph.d.nz, p.ctx->p_row, p.ctx->p_col, r);
+      m = std::max(m, std::max(fft_work_elems(a, 128 / es), fft_work_elems(b, 128 / es)));
+   }
+   return (size_t)es * (size_t)m;
+}
+
+// The same chain when the peers' work buffers are mapped (p2p.cpp): every producer writes each block -- its own
+// included -- straight into the DESTINATION rank's buffer, at the displacement where that rank's consumer expects
+// the block from this rank.  There is no exchange step and no send buffer; two buffers alternate.  Flags order the
+// ranks: "ready" before a producer may write into a peer, "done" before a consumer may read what peers wrote.
+static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
+{
+   Ctx *ctx = p.ctx;
+   const int es = p.f64 ? 16 : 8;
+   const int padq = 128 / es;
+   PieceMap cur = fft_user_map(dc, st[0].pencil, in);
+   for (int s = 0; s < 3; s++) {
+      const int pen = st[s].pencil, mode = st[s].mode;
+      const bool last = (s == 2);
+      const int passthrough = (mode == MODE_C2C && p.skip[pen]) ? 1 : 0;
+      PieceMap om{};
+      void *rptr = nullptr;
+      if (mode == MODE_R2C) rptr = in;
+      int np = 1, me = 0;
+      bool col = false;
+      uint32_t epoch = 0;
+      const int w = s & 1;
+      if (last) {
+         if (mode == MODE_C2R) rptr = out;
+         else om = fft_user_map(dc, pen, out);
+      } else {
+         const int nxt = st[s + 1].pencil;
+         LinkSide L;
+         fft_link_side(dc, pen, nxt, padq, L);
+         np = L.np;
+         me = L.me;
+         col = (pen == 0 || nxt == 0);
+         om.np = np;
+         for (int m = 0; m < np; m++) {
+            const int prank = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
+            Decomp dm;
+            decomp_init(dm, dc.nx, dc.ny, dc.nz, ctx->p_row, ctx->p_col, prank);
+            LinkSide R;
+            fft_link_side(dm, nxt, pen, padq, R); // the consumer side on the destination rank
+            D2D_REQUIRE(R.cnt[me] == L.cnt[m], "peer-store: block sizes of the two sides disagree");
+            char *base = (char *)(m == me ? ctx->work[w] : p2p_peer_work(ctx, w, prank));
+            const size_t cap = m == me ? ctx->work_bytes[w] : p2p_peer_bytes(ctx, w, prank);
+            D2D_REQUIRE(base != nullptr && (size_t)es * (size_t)(R.disp[me] + R.cnt[me]) <= cap, "peer-store: destination buffer too small");
+            om.e0[m] = L.e0[m];
+            om.ptr[m] = base + (size_t)es * R.disp[me];
+            om.se[m] = L.se[m]; om.sa[m] = L.sa[m]; om.sb[m] = L.sb[m];
+         }
+         om.e0[np] = L.e0[np];
+         if (np > 1) {
+            ProfScope ps(ctx, "p2p_ready");
+            epoch = p2p_next_epoch(ctx);
+            for (int k = 1; k < np; k++) {
+               const int m = (me + k) % np;
+               p2p_signal(ctx, col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m), 0, epoch);
+            }
+            for (int k = 1; k < np; k++) {
+               const int m = (me + k) % np;
+               p2p_wait(ctx, col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m), 0, epoch);
+            }
+         }
+      }
+      run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+      if (last) break;
+      const int nxt = st[s + 1].pencil;
+      if (np > 1) {
+         ProfScope ps(ctx, "p2p_done");
+         for (int k = 1; k < np; k++) {
+            const int m = (me + k) % np;
+            p2p_signal(ctx, col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m), 1, epoch);
+         }
+         for (int k = 1; k < np; k++) {
+            const int m = (me + k) % np;
+            p2p_wait(ctx, col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m), 1, epoch);
+         }
+      }
+      // consumer: every block (the one this rank wrote for itself included) sits in this rank's buffer w
+      LinkSide C;
+      fft_link_side(dc, nxt, pen, padq, C);
+      cur = PieceMap{};
+      cur.np = C.np;
+      for (int m = 0; m < C.np; m++) {
+         cur.e0[m] = C.e0[m];
+         cur.ptr[m] = (char *)ctx->work[w] + (size_t)es * C.disp[m];
+         cur.se[m] = C.se[m]; cur.sa[m] = C.sa[m]; cur.sb[m] = C.sb[m];
+      }
+      cur.e0[C.np] = C.e0[C.np];
+   }
+}
+
 static void reserve_all(Plan &p)
 {
    // grow the context's work buffers once, at plan time (never inside the timed path)
-   const int es = p.f64 ? 16 : 8;
-   const size_t wb = (size_t)es * std::max(fft_work_elems(p.sp.d, 128 / es), fft_work_elems(p.ph.d, 128 / es));
+   const size_t wb = uniform_work_bytes(p);
    const bool multi = p.ctx->nranks > 1;
    p.ctx->reserve(0, wb);
    p.ctx->reserve(1, wb);
    if (multi) p.ctx->reserve(2, wb);
+   p2p_publish(p.ctx); // collective (no-op for a single rank / in-process groups)
 }
 
 Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])

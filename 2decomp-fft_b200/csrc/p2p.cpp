@@ -1,0 +1,168 @@
+// p2p.cpp -- peer-memory plumbing for the fused FFT + exchange path (one process per GPU, NVLink/NVSwitch).
+//
+// Inside decomp_2d_fft_3d the all-to-all of a transpose (src/decomp_2d_nccl.f90:214-473 in the reference: grouped
+// ncclSend/ncclRecv after a pack pass) disappears as a separate step: the store map of the producing FFT kernel points
+// piece m straight INTO RANK m's receive buffer (CUDA-IPC mapped), so the transfer happens tile by tile while the
+// kernel computes.  This file provides what that needs:
+//   * exchange of cudaIpcMemHandle_t of the work buffers and of a small flag array (all-gather over the transport),
+//   * stream-ordered flags (cuStreamWriteValue32 / cuStreamWaitValue32 on peer-mapped memory):
+//       ready_from[r] >= e : rank r's stream reached the producer of exchange e  -> its receive buffer may be written
+//       done_from[r]  >= e : rank r's producer kernel of exchange e completed    -> its block has landed here
+// No host synchronisation, no SMs spent on communication.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.h"
+
+namespace d2d {
+
+namespace {
+typedef CUresult (*WriteValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+void *driver_fn(const char *name)
+{
+   void *p = nullptr;
+   cudaDriverEntryPointQueryResult q;
+   if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+   return p;
+}
+
+struct Published {
+   cudaIpcMemHandle_t work[kWorkBuffers];
+   unsigned long long bytes[kWorkBuffers];
+   cudaIpcMemHandle_t flags;
+   int device;
+   int ok;
+};
+} // namespace
+
+struct P2P {
+   int nranks = 0, rank = 0;
+   bool ok = false;
+   void *peer_work[kWorkBuffers][kMaxRanks] = {};
+   size_t peer_bytes[kWorkBuffers][kMaxRanks] = {};
+   void *opened[kWorkBuffers][kMaxRanks] = {};
+   uint32_t *flags = nullptr; // local: [0..nranks) ready_from, [nranks..2 nranks) done_from
+   uint32_t *peer_flags[kMaxRanks] = {};
+   void *opened_flags[kMaxRanks] = {};
+   bool flags_published = false;
+   uint32_t epoch = 0;
+   WriteValueFn write_value = nullptr;
+   WaitValueFn wait_value = nullptr;
+};
+
+static void close_work(P2P *p)
+{
+   for (int w = 0; w < kWorkBuffers; w++)
+      for (int r = 0; r < p->nranks; r++) {
+         if (p->opened[w][r]) cudaIpcCloseMemHandle(p->opened[w][r]);
+         p->opened[w][r] = nullptr;
+         p->peer_work[w][r] = nullptr;
+         p->peer_bytes[w][r] = 0;
+      }
+}
+
+void p2p_destroy(P2P *p)
+{
+   if (!p) return;
+   close_work(p);
+   for (int r = 0; r < p->nranks; r++)
+      if (p->opened_flags[r]) cudaIpcCloseMemHandle(p->opened_flags[r]);
+   if (p->flags) cudaFree(p->flags);
+   delete p;
+}
+
+// Collective over all ranks of the context: publish the current work buffers (and, once, the flag array).
+// Must be called by every rank in the same order (plan creation is collective, like communicator creation).
+void p2p_publish(Ctx *ctx)
+{
+   static const bool enabled = getenv("D2D_P2P") ? atoi(getenv("D2D_P2P")) != 0 : true;
+   if (!enabled || ctx->nranks <= 1 || !ctx->tr || ctx->tr->kind() != D2D_TRANSPORT_NCCL) return;
+   D2D_REQUIRE(ctx->nranks <= kMaxRanks, "too many ranks for the peer-memory path");
+   if (!ctx->p2p) {
+      ctx->p2p = new P2P();
+      ctx->p2p->nranks = ctx->nranks;
+      ctx->p2p->rank = ctx->rank;
+      ctx->p2p->write_value = (WriteValueFn)driver_fn("cuStreamWriteValue32");
+      ctx->p2p->wait_value = (WaitValueFn)driver_fn("cuStreamWaitValue32");
+      D2D_CHECK_CUDA(cudaMalloc((void **)&ctx->p2p->flags, 2 * kMaxRanks * sizeof(uint32_t)));
+      D2D_CHECK_CUDA(cudaMemset(ctx->p2p->flags, 0, 2 * kMaxRanks * sizeof(uint32_t)));
+   }
+   P2P *p = ctx->p2p;
+   D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+   close_work(p);
+   Published mine;
+   memset(&mine, 0, sizeof(mine));
+   mine.ok = (p->write_value && p->wait_value) ? 1 : 0;
+   mine.device = ctx->device;
+   for (int w = 0; w < kWorkBuffers; w++) {
+      mine.bytes[w] = ctx->work_bytes[w];
+      if (ctx->work[w] && cudaIpcGetMemHandle(&mine.work[w], ctx->work[w]) != cudaSuccess) mine.ok = 0;
+   }
+   if (cudaIpcGetMemHandle(&mine.flags, p->flags) != cudaSuccess) mine.ok = 0;
+   cudaGetLastError();
+   std::vector<Published> all(p->nranks);
+   ctx->tr->allgather(&mine, all.data(), sizeof(Published), ctx->stream);
+   int ok = 1;
+   for (int r = 0; r < p->nranks; r++) ok = ok && all[r].ok;
+   if (ok) {
+      for (int r = 0; r < p->nranks && ok; r++) {
+         if (r == p->rank) {
+            for (int w = 0; w < kWorkBuffers; w++) { p->peer_work[w][r] = ctx->work[w]; p->peer_bytes[w][r] = ctx->work_bytes[w]; }
+            p->peer_flags[r] = p->flags;
+            continue;
+         }
+         for (int w = 0; w < kWorkBuffers && ok; w++) {
+            if (!all[r].bytes[w]) continue;
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r].work[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            p->opened[w][r] = q;
+            p->peer_work[w][r] = q;
+            p->peer_bytes[w][r] = (size_t)all[r].bytes[w];
+         }
+         if (ok && !p->flags_published) {
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+            else { p->opened_flags[r] = q; p->peer_flags[r] = (uint32_t *)q; }
+         }
+      }
+      cudaGetLastError();
+   }
+   // every rank must take the same path: agree on the outcome
+   std::vector<int> oks(p->nranks);
+   ctx->tr->allgather(&ok, oks.data(), sizeof(int), ctx->stream);
+   for (int r = 0; r < p->nranks; r++) ok = ok && oks[r];
+   if (ok) p->flags_published = true;
+   else close_work(p);
+   p->ok = ok != 0;
+}
+
+bool p2p_active(const Ctx *ctx) { return ctx->p2p && ctx->p2p->ok; }
+void p2p_invalidate(Ctx *ctx)
+{
+   if (ctx->p2p) ctx->p2p->ok = false;
+}
+void *p2p_peer_work(const Ctx *ctx, int w, int rank) { return ctx->p2p->peer_work[w][rank]; }
+size_t p2p_peer_bytes(const Ctx *ctx, int w, int rank) { return ctx->p2p->peer_bytes[w][rank]; }
+uint32_t p2p_next_epoch(Ctx *ctx) { return ++ctx->p2p->epoch; }
+
+// tell `peer` that this rank's stream reached the point `which` (0 ready, 1 done) of exchange `epoch`
+void p2p_signal(Ctx *ctx, int peer, int which, uint32_t epoch)
+{
+   P2P *p = ctx->p2p;
+   uint32_t *addr = p->peer_flags[peer] + which * p->nranks + p->rank;
+   CUresult r = p->write_value((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)addr, epoch, 0);
+   D2D_REQUIRE(r == CUDA_SUCCESS, "cuStreamWriteValue32 failed");
+}
+// make this rank's stream wait until `peer` signalled `which` for exchange `epoch`
+void p2p_wait(Ctx *ctx, int peer, int which, uint32_t epoch)
+{
+   P2P *p = ctx->p2p;
+   uint32_t *addr = p->flags + which * p->nranks + peer;
+   CUresult r = p->wait_value((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)addr, epoch, CU_STREAM_WAIT_VALUE_GEQ);
+   D2D_REQUIRE(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed");
+}
+
+} // namespace d2d

@@ -49,6 +49,17 @@ struct NcclTransport : Transport {
       }
       D2D_CHECK_NCCL(ncclGroupEnd());
    }
+   void allgather(const void *send_host, void *recv_host, size_t bytes, cudaStream_t st) override
+   {
+      void *dbuf = nullptr;
+      D2D_CHECK_CUDA(cudaMalloc(&dbuf, bytes * (size_t)(nranks + 1)));
+      char *dsend = (char *)dbuf + bytes * (size_t)nranks;
+      D2D_CHECK_CUDA(cudaMemcpyAsync(dsend, send_host, bytes, cudaMemcpyHostToDevice, st));
+      D2D_CHECK_NCCL(ncclAllGather(dsend, dbuf, bytes, ncclInt8, comm, st));
+      D2D_CHECK_CUDA(cudaMemcpyAsync(recv_host, dbuf, bytes * (size_t)nranks, cudaMemcpyDeviceToHost, st));
+      D2D_CHECK_CUDA(cudaStreamSynchronize(st));
+      D2D_CHECK_CUDA(cudaFree(dbuf));
+   }
    void barrier(cudaStream_t st) override
    {
       // a 1-element all-reduce is the cheapest stream-ordered barrier NCCL offers
