@@ -200,6 +200,33 @@ template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> stru
    static constexpr size_t smem_bytes = off_bar + 16;
 };
 
+// Walks the pieces of a map for increasing e: the piece lookup and the (a, b) part of the address are redone only
+// when e crosses into the next piece (store side of multi-rank chains, where every element used to pay a search).
+template <typename T2> struct PieceCursor {
+   const PieceMap &m;
+   long long a, b;
+   int pc, next_e0;
+   T2 *base; // &piece[pc](e = 0, a, b), i.e. ptr - e0 se + a sa + b sb
+   long long se;
+   __device__ __forceinline__ PieceCursor(const PieceMap &m_, long long a_, long long b_) : m(m_), a(a_), b(b_), pc(-1), next_e0(0), base(nullptr), se(0)
+   {
+      load(0);
+   }
+   __device__ __forceinline__ void load(int p)
+   {
+      pc = p;
+      next_e0 = (p + 1 < m.np) ? m.e0[p + 1] : 0x7fffffff;
+      se = m.se[p];
+      base = reinterpret_cast<T2 *>(m.ptr[p]) + a * m.sa[p] + b * m.sb[p] - (long long)m.e0[p] * se;
+   }
+   __device__ __forceinline__ T2 *at(int e)
+   {
+      while (e >= next_e0) load(pc + 1);
+      return base + (long long)e * se;
+   }
+   __device__ __forceinline__ long long sa() const { return m.sa[pc]; }
+};
+
 // ---- the kernel -------------------------------------------------------------------------------------
 template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL, int MINB>
 __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid_constant__ FftArgs2 g2, const __grid_constant__ TmapPack tm)
@@ -421,11 +448,12 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   p += step;
                }
             } else {
+               PieceCursor<T2> cur(g.out, a, b);
 #pragma unroll
                for (int s = 0; s < E; s++) {
                   T2 x = v[s];
                   x.y = flip_sign(x.y, conj_mask);
-                  store_piece<T2>(g.out, j + TPL * s, a, b, x);
+                  *cur.at(j + TPL * s) = x;
                }
             }
          }
@@ -464,7 +492,8 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             if (k <= N / 2 && (s < E / 2 || j == 0)) zn[s] = lsm[padix<PADK>((N - k) % N) * SP];
          }
          late();
-         if (!(g.debug & 1)) {
+         if (!(g.debug & 1) && valid) {
+            PieceCursor<T2> cur(g.out, 2 * a, b);
 #pragma unroll
             for (int s = 0; s <= E / 2; s++) {
                const int k = j + TPL * s;
@@ -473,8 +502,9 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   const T hf = (T)0.5;
                   T2 A = T2{(zk.x + zn[s].x) * hf, (zk.y - zn[s].y) * hf};
                   T2 B = T2{(zk.y + zn[s].y) * hf, (zn[s].x - zk.x) * hf};
-                  if (valid) store_piece<T2>(g.out, k, 2 * a, b, A);
-                  if (v1) store_piece<T2>(g.out, k, 2 * a + 1, b, B);
+                  T2 *q = cur.at(k);
+                  *q = A;
+                  if (v1) q[cur.sa()] = B;
                }
             }
          }

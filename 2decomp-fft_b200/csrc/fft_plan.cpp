@@ -196,6 +196,7 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
       int np = 1, me = 0;
       bool col = false;
       uint32_t epoch = 0;
+      double remote_bytes = 0;
       const int w = s & 1;
       if (last) {
          if (mode == MODE_C2R) rptr = out;
@@ -221,6 +222,7 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
             om.e0[m] = L.e0[m];
             om.ptr[m] = base + (size_t)es * R.disp[me];
             om.se[m] = L.se[m]; om.sa[m] = L.sa[m]; om.sb[m] = L.sb[m];
+            if (m != me) remote_bytes += (double)es * (double)L.cnt[m];
          }
          om.e0[np] = L.e0[np];
          if (np > 1) {
@@ -236,7 +238,13 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
             }
          }
       }
-      run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+      {
+         // the producer kernel IS the exchange: time it a second time under the link's name with the bytes that
+         // leave this GPU, so that the NVLink rate of the fused kernel can be read next to its HBM rate
+         static const char *names[3][3] = {{"", "p2p_x_y", ""}, {"p2p_y_x", "", "p2p_y_z"}, {"", "p2p_z_y", ""}};
+         ProfScope ps(ctx, (!last && np > 1) ? names[pen][st[s + 1].pencil] : "p2p_none", remote_bytes);
+         run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+      }
       if (last) break;
       const int nxt = st[s + 1].pencil;
       if (np > 1) {

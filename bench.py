@@ -304,8 +304,10 @@ def main():
             kern[label] = {"ms": tot / calls, "GBps": by / calls / (tot / calls) / 1e6, "bytes": by / calls, "calls": calls}
     comm = {}
     for label, (tot, calls, by) in prof.items():
-        if label.startswith("a2a_") and calls:
+        # a2a_*: NCCL send/recv exchange; p2p_*: the producer kernel whose stores go to the peers (fused exchange)
+        if (label.startswith("a2a_") or (label.startswith("p2p_") and label[4:] in ("x_y", "y_x", "y_z", "z_y"))) and calls:
             comm[label] = {"ms": tot / calls, "send_GBps": by / calls / (tot / calls) / 1e6, "send_bytes": by / calls}
+    sync_ms = {k: prof[k][0] / args.steps for k in ("p2p_ready", "p2p_done") if k in prof}
     dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["calls"]) if kern else None
     traffic = None
     try:
@@ -321,6 +323,8 @@ def main():
                     "bytes_per_launch": kern[dom]["bytes"], "ms_per_launch": kern[dom]["ms"],
                     "all_kernels": {k: {"ms": round(v["ms"], 4), "GBps": round(v["GBps"], 1), "frac": round(v["GBps"] / peak, 3)}
                                     for k, v in kern.items()}}
+        if sync_ms:
+            roofline["flag_wait_ms_per_step"] = {k: round(v, 4) for k, v in sync_ms.items()}
         if comm:
             roofline["exchanges"] = {k: {"ms": round(v["ms"], 4), "send_GBps": round(v["send_GBps"], 1),
                                          "frac_of_900": round(v["send_GBps"] / 900.0, 3)} for k, v in comm.items()}
