@@ -1,0 +1,157 @@
+// fft_any.cu -- host side of the arbitrary-length FFT kernel (fft_any.cuh): factorisation, geometry,
+// the table of n-th roots of unity, launch.  Used by run_stage (fft_plan.cpp) for every transform length
+// without a compiled power-of-two kernel.
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.h"
+#include "fft_any.cuh"
+
+namespace d2d {
+
+namespace {
+struct RootKey {
+   int device, n, f64;
+   bool operator<(const RootKey &o) const { return std::tie(device, n, f64) < std::tie(o.device, o.n, o.f64); }
+};
+std::mutex g_root_mutex;
+std::map<RootKey, void *> g_roots;
+
+constexpr size_t kAnySmemBudget = 200 * 1024;
+
+// W[k] = exp(-2 pi i k / n): octant-reduced so that every entry is accurate to the last bit or so
+const void *roots_for(int device, int n, int f64)
+{
+   std::lock_guard<std::mutex> lk(g_root_mutex);
+   RootKey key{device, n, f64};
+   auto it = g_roots.find(key);
+   if (it != g_roots.end()) return it->second;
+   std::vector<double> hd(2 * (size_t)n);
+   const long double pi = 3.14159265358979323846264338327950288L;
+   for (int k = 0; k < n; k++) {
+      // angle = 2 pi k / n, reduced to [0, pi/4] through the symmetries of the circle (exact integer arithmetic on 8k/n)
+      long long num = 8LL * k; // angle = (pi/4) * num / n
+      const int oct = (int)(num / n);
+      long long rem = num - (long long)oct * n; // in [0, n)
+      long double c, s;
+      if (oct & 1) { // odd octant: measure from the end of the octant
+         const long double t = (pi / 4) * (long double)(n - rem) / (long double)n;
+         c = sinl(t); s = cosl(t);
+      } else {
+         const long double t = (pi / 4) * (long double)rem / (long double)n;
+         c = cosl(t); s = sinl(t);
+      }
+      // (c, s) = (cos, sin) of the angle folded into the first quadrant's two octants; unfold by quadrant
+      long double cc, ss;
+      switch (oct >> 1) {
+      case 0: cc = c; ss = s; break;
+      case 1: cc = -s; ss = c; break;
+      case 2: cc = -c; ss = -s; break;
+      default: cc = s; ss = -c; break;
+      }
+      hd[2 * k] = (double)cc;
+      hd[2 * k + 1] = (double)(-ss);
+   }
+   void *dptr = nullptr;
+   const size_t bytes = (size_t)n * (f64 ? 16 : 8);
+   D2D_CHECK_CUDA(cudaMalloc(&dptr, bytes));
+   if (f64) {
+      D2D_CHECK_CUDA(cudaMemcpy(dptr, hd.data(), bytes, cudaMemcpyHostToDevice));
+   } else {
+      std::vector<float> hf(hd.begin(), hd.end());
+      D2D_CHECK_CUDA(cudaMemcpy(dptr, hf.data(), bytes, cudaMemcpyHostToDevice));
+   }
+   g_roots[key] = dptr;
+   return dptr;
+}
+
+template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, size_t smem, cudaStream_t st)
+{
+   auto kern = fft_any_kernel<T, MODE>;
+   static size_t smem_set = 0;
+   static int sms = 0;
+   if (smem > 48 * 1024 && smem > smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemBudget + 28 * 1024);
+      if (e != cudaSuccess) return e;
+      smem_set = kAnySmemBudget + 28 * 1024;
+   }
+   if (!sms) {
+      int dev = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+   }
+   int per_sm = 0;
+   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAnyThreads, smem);
+   if (e != cudaSuccess) return e;
+   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+   const long long total = (long long)ga.a.na * ga.a.nb;
+   const long long groups = (total + ga.lines - 1) / ga.lines;
+   if (groups <= 0) return cudaSuccess;
+   const long long resident = (long long)sms * per_sm;
+   const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
+   kern<<<blocks, kAnyThreads, smem, st>>>(ga);
+   return cudaGetLastError();
+}
+} // namespace
+
+// factors of n in pass order: 4s, then a 2, then the odd primes in increasing order
+int fft_any_factorize(int n, int *radix, int maxp)
+{
+   int np = 0;
+   auto push = [&](int r) {
+      if (np < maxp) radix[np] = r;
+      np++;
+   };
+   while (n % 4 == 0) { push(4); n /= 4; }
+   if (n % 2 == 0) { push(2); n /= 2; }
+   for (int f = 3; (long long)f * f <= n; f += 2)
+      while (n % f == 0) { push(f); n /= f; }
+   if (n > 1) push(n);
+   return np;
+}
+
+void fft_any_release_all()
+{
+   std::lock_guard<std::mutex> lk(g_root_mutex);
+   for (auto &kv : g_roots) cudaFree(kv.second);
+   g_roots.clear();
+}
+
+// largest transform length the shared-memory kernel takes (one line per block, two buffers + the root table)
+int fft_any_max_n(int f64) { return (int)(kAnySmemBudget / (3 * (size_t)(f64 ? 16 : 8))) - 1; }
+
+cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
+{
+   const int n = g.n;
+   const size_t ces = f64 ? 16 : 8;
+   D2D_REQUIRE(n >= 1 && n <= fft_any_max_n(f64),
+               "transform length " + std::to_string(n) + " is not supported (neither a compiled power of two nor <= " +
+                  std::to_string(fft_any_max_n(f64)) + ")");
+   FftArgsAny ga{};
+   ga.a = g;
+   ga.a.tw = roots_for(ctx->device, n, f64);
+   ga.npass = fft_any_factorize(n, ga.radix, kMaxAnyPass);
+   D2D_REQUIRE(ga.npass <= kMaxAnyPass, "too many factors");
+   ga.pitch = n | 1;
+   // which axis is unit-stride on each side
+   if (mode == MODE_R2C) ga.in_fast_a = (g.rsa == 1 && g.rse != 1);
+   else ga.in_fast_a = (g.in.sa[0] == 1 && g.in.se[0] != 1);
+   if (mode == MODE_C2R) ga.out_fast_a = (g.rsa == 1 && g.rse != 1);
+   else ga.out_fast_a = (g.out.sa[0] == 1 && g.out.se[0] != 1);
+   // lines per block: 128-byte rows when lines are strided, and enough elements to keep 256 threads busy
+   const int want_rows = (int)(128 / ces);
+   int lines = std::max(want_rows, (2048 + n - 1) / n);
+   const long long max_lines = ((long long)(kAnySmemBudget / ces) - n) / (2LL * ga.pitch);
+   lines = (int)std::min<long long>(lines, std::max<long long>(1, max_lines));
+   lines = (int)std::min<long long>(lines, std::max<long long>(1, (long long)g.na * g.nb));
+   ga.lines = lines;
+   const size_t smem = ces * ((size_t)n + 2 * (size_t)lines * ga.pitch);
+   if (mode == MODE_C2C) return f64 ? launch_any<double, MODE_C2C>(ga, smem, ctx->stream) : launch_any<float, MODE_C2C>(ga, smem, ctx->stream);
+   if (mode == MODE_R2C) return f64 ? launch_any<double, MODE_R2C>(ga, smem, ctx->stream) : launch_any<float, MODE_R2C>(ga, smem, ctx->stream);
+   return f64 ? launch_any<double, MODE_C2R>(ga, smem, ctx->stream) : launch_any<float, MODE_C2R>(ga, smem, ctx->stream);
+}
+
+} // namespace d2d

@@ -15,6 +15,7 @@
 namespace d2d {
 
 bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_t *err);
+cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode); // fft_any.cu: lengths without a compiled kernel
 
 struct Plan {
    Ctx *ctx;
@@ -84,15 +85,15 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    const bool line_like = kind == KIND_TILE && ((mode == MODE_C2C && in.se[0] == 1) || (mode == MODE_R2C && g.rse == 1));
    if (!k && line_like) k = fft_find(n, f64, kind, mode, pairvec, 1);
    if (!k) k = fft_find(n, f64, kind, mode, pairvec);
-   D2D_REQUIRE(k != nullptr, "transform length " + std::to_string(n) + " is not supported by the compiled kernels");
-   g.tw = twiddles_for(ctx->device, n, f64);
+   if (k) g.tw = twiddles_for(ctx->device, n, f64);
    static const char *axes = "xyz";
    char label[32];
    snprintf(label, sizeof(label), "fft_%s_%c%s", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil],
             (mode == MODE_C2C && chain) ? (backward ? "_bwd" : "_fwd") : "");
    ProfScope ps(ctx, label, bytes);
    cudaError_t e = cudaSuccess;
-   if (!fft_v2_try_launch(ctx, g, f64, mode, &e)) e = k->launch(g, ctx->stream);
+   if (!k) e = fft_any_launch(ctx, g, f64, mode); // not a compiled power of two: mixed-radix shared-memory kernel
+   else if (!fft_v2_try_launch(ctx, g, f64, mode, &e)) e = k->launch(g, ctx->stream);
    if (e != cudaSuccess) throw Error(1000 + (int)e, std::string("FFT kernel launch failed: ") + cudaGetErrorString(e));
    ctx->launches++;
 }
