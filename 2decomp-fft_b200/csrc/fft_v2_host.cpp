@@ -121,8 +121,10 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
    if (mode == MODE_C2R) tile_out = g.rsa == 1 && g.rse != 1;
    else tile_out = g.out.sa[0] == 1 && g.out.se[0] != 1;
    static const int rb_all = env_int("D2D_V2_ROWBYTES", 64), rb_tout = env_int("D2D_V2_ROWBYTES_TILEOUT", 0);
+   static const int rb_r2c = env_int("D2D_V2_ROWBYTES_R2C", 0); // experiments: row bytes of r2c stages whose input is a tile
    // default: 128-byte rows for fp64 tile-out stages (one block of 512 threads per SM); fp32 would need 1024 threads
-   const int want = tile_out ? (rb_tout ? rb_tout : (f64 ? 128 : 64)) : rb_all;
+   int want = tile_out ? (rb_tout ? rb_tout : (f64 ? 128 : 64)) : rb_all;
+   if (rb_r2c && mode == MODE_R2C && inl == IN_TILE) want = rb_r2c;
    const FftKernelInfo *k = fft_find_v2(g.n, f64, mode, inl, want);
    if (!k) k = fft_find_v2(g.n, f64, mode, inl, 64);
    if (!k) return false;

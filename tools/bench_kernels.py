@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--shape", default=None, help="nx,ny,nz (default n,n,n)")
     ap.add_argument("--only1d", action="store_true")
+    ap.add_argument("--only3d", action="store_true")
+    ap.add_argument("--fmt", default="ZX", help="which 3-D pairs: Z, X or ZX")
     ap.add_argument("--axes", default="0,1,2")
     ap.add_argument("--oop", action="store_true", help="1-D stages out of place")
     ap.add_argument("--warm", type=int, default=2)
@@ -38,11 +40,12 @@ def main():
     d2d = p.decomp_2d_init(*shape, 1, 1)
     d2d.set_blocking(False)
     nx, ny, nz = shape
-    cz = d2d.alloc_x(cdt)  # (nx,ny,nz) complex
-    cz.real.normal_()
+    cz = None if a.only3d else d2d.alloc_x(cdt)  # (nx,ny,nz) complex
+    if cz is not None:
+        cz.real.normal_()
     co = d2d.alloc_x(cdt) if a.oop else None
     res = {}
-    for axis in [int(x) for x in a.axes.split(',')]:
+    for axis in ([] if a.only3d else [int(x) for x in a.axes.split(',')]):
         for _ in range(a.warm):
             d2d.c2c_1m(cz, axis, -1, out=co)
         d2d.sync()
@@ -59,7 +62,7 @@ def main():
     del cz
     torch.cuda.empty_cache()
     # full 3-D pair, PHYSICAL_IN_Z (headline) and PHYSICAL_IN_X
-    for fmt, name in (() if a.only1d else ((p.PHYSICAL_IN_Z, "Z"), (p.PHYSICAL_IN_X, "X"))):
+    for fmt, name in (() if a.only1d else [(f, nm) for f, nm in ((p.PHYSICAL_IN_Z, "Z"), (p.PHYSICAL_IN_X, "X")) if nm in a.fmt]):
         eng = p.decomp_2d_fft_init(fmt, dtype=rdt)
         a_in = (d2d.alloc_z if fmt == p.PHYSICAL_IN_Z else d2d.alloc_x)(rdt, eng.ph)
         a_out = (d2d.alloc_x if fmt == p.PHYSICAL_IN_Z else d2d.alloc_z)(cdt, eng.sp)
