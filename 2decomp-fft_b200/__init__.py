@@ -29,6 +29,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd2dfft_b200.so")
+if os.environ.get("D2D_B200_LIB"):  # experiments: an alternative build of the same library (Makefile VARIANT=...)
+    LIB_PATH = os.environ["D2D_B200_LIB"]
 
 # src/decomp_2d_constants.f90:86-93
 DECOMP_2D_FFT_FORWARD = -1
@@ -96,6 +98,7 @@ def lib():
         l.d2d_ctx_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         l.d2d_group_create.argtypes = [C.c_void_p, C.c_int]
         l.d2d_group_destroy.argtypes = [C.c_void_p]
+        l.d2d_group_abort.argtypes = [C.c_void_p]
         l.d2d_decomp_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.d2d_decomp_create_for_rank.argtypes = [C.c_int] * 6 + [C.c_void_p]
         l.d2d_decomp_destroy.argtypes = [C.c_void_p]
@@ -175,6 +178,11 @@ class Group:
         self._h = C.c_void_p()
         self.nranks = nranks
         _check(lib().d2d_group_create(C.byref(self._h), nranks))
+
+    def abort(self):
+        """A rank failed: wake the ranks waiting for it in an exchange (they raise Decomp2dError)."""
+        if self._h:
+            lib().d2d_group_abort(self._h)
 
     def destroy(self):
         if self._h:

@@ -94,6 +94,13 @@ int d2d_group_destroy(d2d_group *grp)
    if (grp) { group_destroy(grp->g); delete grp; }
    D2D_CATCH
 }
+int d2d_group_abort(d2d_group *grp)
+{
+   D2D_TRY
+   D2D_REQUIRE(grp != nullptr, "null group");
+   group_abort(grp->g);
+   D2D_CATCH
+}
 int d2d_ctx_create_in_group(d2d_ctx **ctx, d2d_group *grp, int rank, int p_row, int p_col, int device)
 {
    D2D_TRY

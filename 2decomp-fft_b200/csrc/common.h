@@ -84,6 +84,7 @@ void nccl_unique_id(unsigned char id[128]);
 struct Group;
 Group *group_create(int nranks);
 void group_destroy(Group *);
+void group_abort(Group *); // wake every rank waiting in the group's barrier with an error (a rank failed)
 Transport *make_local_transport(Group *g, int rank);
 
 struct ProfEntry {

@@ -173,23 +173,33 @@ struct Group {
    std::condition_variable cv;
    int waiting = 0;
    long long generation = 0;
+   bool aborted = false; // a rank failed: every present and future barrier throws instead of waiting for it
    std::vector<std::vector<PeerXfer>> posted;
    explicit Group(int n_) : n(n_), posted(n_) {}
    void barrier()
    {
       std::unique_lock<std::mutex> lk(m);
       const long long gen = generation;
+      if (aborted) throw Error(3, "rank group aborted: another rank of this group failed");
       if (++waiting == n) {
          waiting = 0;
          generation++;
          cv.notify_all();
       } else {
-         cv.wait(lk, [&] { return generation != gen; });
+         cv.wait(lk, [&] { return generation != gen || aborted; });
+         if (generation == gen) throw Error(3, "rank group aborted: another rank of this group failed");
       }
+   }
+   void abort()
+   {
+      std::lock_guard<std::mutex> lk(m);
+      aborted = true;
+      cv.notify_all();
    }
 };
 Group *group_create(int nranks) { return new Group(nranks); }
 void group_destroy(Group *g) { delete g; }
+void group_abort(Group *g) { g->abort(); }
 
 namespace {
 struct LocalTransport : Transport {

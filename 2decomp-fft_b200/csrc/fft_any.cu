@@ -19,7 +19,8 @@ struct RootKey {
 std::mutex g_root_mutex;
 std::map<RootKey, void *> g_roots;
 
-constexpr size_t kAnySmemBudget = 200 * 1024;
+constexpr size_t kAnySmemBudget = 200 * 1024; // what the geometry may use
+constexpr size_t kAnySmemMax = 227 * 1024;    // opt-in limit of sm_100a
 
 // W[k] = exp(-2 pi i k / n): octant-reduced so that every entry is accurate to the last bit or so
 const void *roots_for(int device, int n, int f64)
@@ -73,9 +74,9 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
    static size_t smem_set = 0;
    static int sms = 0;
    if (smem > 48 * 1024 && smem > smem_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemBudget + 28 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemMax);
       if (e != cudaSuccess) return e;
-      smem_set = kAnySmemBudget + 28 * 1024;
+      smem_set = kAnySmemMax;
    }
    if (!sms) {
       int dev = 0;

@@ -181,6 +181,43 @@ template <typename T> struct Bfly<T, 16> {
    static constexpr int out_idx(int r) { return 4 * (r & 3) + (r >> 2); }
 };
 
+template <typename T> struct Bfly<T, 32> {
+   using T2 = typename Vec2<T>::type;
+   // DIF split 2 x 16: X[2m] = DFT16(x_k + x_{k+16})[m], X[2m+1] = DFT16((x_k - x_{k+16}) W32^k)[m]
+   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   {
+      // W32^k = (cos(k pi/16), -sin(k pi/16)), k = 1..15
+      constexpr T c1 = (T)0.98078528040323044913, s1 = (T)0.19509032201612826785; // pi/16
+      constexpr T c2 = Consts<T>::c8, s2 = Consts<T>::s8;                           // 2 pi/16
+      constexpr T c3 = (T)0.83146961230254523708, s3 = (T)0.55557023301960222474; // 3 pi/16
+      constexpr T h = Consts<T>::rsqrt2;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+         T2 a = v[B + k * S], b = v[B + (k + 16) * S];
+         v[B + k * S] = cadd(a, b);
+         v[B + (k + 16) * S] = csub(a, b);
+      }
+      v[B + 17 * S] = cmul(v[B + 17 * S], T2{c1, -s1});
+      v[B + 18 * S] = cmul(v[B + 18 * S], T2{c2, -s2});
+      v[B + 19 * S] = cmul(v[B + 19 * S], T2{c3, -s3});
+      { T2 t = v[B + 20 * S]; v[B + 20 * S] = T2{(t.x + t.y) * h, (t.y - t.x) * h}; }
+      v[B + 21 * S] = cmul(v[B + 21 * S], T2{s3, -c3});
+      v[B + 22 * S] = cmul(v[B + 22 * S], T2{s2, -c2});
+      v[B + 23 * S] = cmul(v[B + 23 * S], T2{s1, -c1});
+      v[B + 24 * S] = mul_mi(v[B + 24 * S]);
+      v[B + 25 * S] = cmul(v[B + 25 * S], T2{-s1, -c1});
+      v[B + 26 * S] = cmul(v[B + 26 * S], T2{-s2, -c2});
+      v[B + 27 * S] = cmul(v[B + 27 * S], T2{-s3, -c3});
+      { T2 t = v[B + 28 * S]; v[B + 28 * S] = T2{(t.y - t.x) * h, -(t.x + t.y) * h}; }
+      v[B + 29 * S] = cmul(v[B + 29 * S], T2{-c3, -s3});
+      v[B + 30 * S] = cmul(v[B + 30 * S], T2{-c2, -s2});
+      v[B + 31 * S] = cmul(v[B + 31 * S], T2{-c1, -s1});
+      Bfly<T, 16>::template run<B, S>(v);
+      Bfly<T, 16>::template run<B + 16 * S, S>(v);
+   }
+   static constexpr int out_idx(int r) { return (r & 1) * 16 + Bfly<T, 16>::out_idx(r >> 1); }
+};
+
 // ---- radix plans for power-of-two n: E elements per thread, T = n/E threads per line ------------
 template <int N> struct Pow2Plan;
 #define D2D_PLAN(N_, E_, A, B, C, D)                                                                                   \
@@ -196,8 +233,16 @@ D2D_PLAN(32, 8, 8, 4, 1, 1)
 D2D_PLAN(64, 8, 8, 8, 1, 1)
 D2D_PLAN(128, 16, 16, 8, 1, 1)
 D2D_PLAN(256, 16, 16, 16, 1, 1)
+#ifdef D2D_PLAN1024_R32
+D2D_PLAN(512, 32, 32, 16, 1, 1)
+#else
 D2D_PLAN(512, 8, 8, 8, 8, 1)
+#endif
+#ifdef D2D_PLAN1024_R32
+D2D_PLAN(1024, 32, 32, 32, 1, 1) // two passes, ONE shared-memory exchange (experiment: halves the exchange traffic)
+#else
 D2D_PLAN(1024, 16, 16, 16, 4, 1)
+#endif
 D2D_PLAN(2048, 16, 16, 16, 8, 1)
 D2D_PLAN(4096, 16, 16, 16, 16, 1)
 D2D_PLAN(8192, 16, 16, 16, 16, 2)

@@ -32,6 +32,15 @@ namespace d2d {
 
 enum InLayout { IN_TILE = 0, IN_LINE = 1 };
 
+// Build-time switches of the two most recent kernel changes (make VARIANT=_safe EXTRA=-DD2D_V2_SAFE builds the library
+// without them, for A/B runs): the r2c mirror exchange in the tail of X and the even/odd split of real line pairs
+// across the two landing zones.
+#ifdef D2D_V2_SAFE
+constexpr bool kV2Mirror = false, kV2SplitPairs = false;
+#else
+constexpr bool kV2Mirror = true, kV2SplitPairs = true;
+#endif
+
 constexpr int kMaxTmaps = 16;
 constexpr int kMaxLoadOps = 40;
 
@@ -185,7 +194,8 @@ template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> stru
    static constexpr int line_esize = (MODE == MODE_R2C) ? (int)sizeof(T) : (int)sizeof(T2);
    // pitch chosen so that the TX lines read by a quarter/half warp fall into distinct banks
    static constexpr int line_pitch_elems = (MODE == MODE_C2C)   ? N + (bankq / TX > 0 ? bankq / TX : 1)
-                                           : (MODE == MODE_R2C) ? N + 16 / (int)sizeof(T) * (TX >= 4 ? 2 : 4)
+                                           : (MODE == MODE_R2C) ? (kV2SplitPairs ? N + ((128 / (int)sizeof(T)) / TX > 2 ? (128 / (int)sizeof(T)) / TX : 2)
+                                                                                 : N + 16 / (int)sizeof(T) * (TX >= 4 ? 2 : 4))
                                                                 : NH;
    static constexpr size_t line_pitch = ((size_t)line_pitch_elems * line_esize + 15) / 16 * 16;
    static constexpr size_t l_sub = (((INL == IN_TILE) ? (size_t)rows_early * row_bytes : (size_t)lines_early * line_pitch) + 127) / 128 * 128;
@@ -193,6 +203,12 @@ template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> stru
    static constexpr size_t l_bytes = l_sub * LY;
    static constexpr int late_skew = (INL == IN_LINE && MODE == MODE_C2C) ? (bankq / 2) * (int)sizeof(T2) : 0; // bank skew of the late zone
    static constexpr bool late_fits = late_sub + late_skew <= x_sub; // the late half of a tile lands in the exchange buffer of its sub-tile
+   // R2C epilogue: only the upper half of Z (positions n/2..n-1) has to change hands to separate the two spectra.  It is
+   // exchanged through the TAIL of the exchange buffer, behind the late landing zone, so that the late half of the next
+   // tile can be requested right after the last pass exchange (as in C2C) instead of after the epilogue.
+   static constexpr size_t mir_off = (late_skew + late_sub + 15) / 16 * 16;
+   static constexpr size_t mir_bytes = (size_t)(padix<PADK>(N / 2 - 1) + 1) * TX * sizeof(T2);
+   static constexpr bool mirror_fits = kV2Mirror && (MODE == MODE_R2C) && (P::E % 2 == 0) && (mir_off + mir_bytes <= x_sub);
    static constexpr size_t tw_bytes = ((size_t)PlanInfo2<P>::tw_total * sizeof(T2) + 15) / 16 * 16;
    static constexpr size_t off_x = l_bytes;
    static constexpr size_t off_tw = off_x + x_bytes;
@@ -298,20 +314,25 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          }
       } else {
          if (tid < 32) {
-            // one bulk copy per (line, piece); lines [lbase, lbase + nl) of each sub-tile belong to this half
+            // one bulk copy per (line, piece).  C2C: lines [lbase, lbase + nl) of each sub-tile belong to this half.
+            // Real modes: the early zone takes the EVEN input lines (first line of every pair), the late zone the ODD
+            // ones, so that the TX lines read together by a quarter warp sit at odd multiples of the pitch apart
+            // (conflict-free; with pairs stored next to each other they were 2 pitches apart: 2-way conflicts).
+            constexpr bool SPLIT = kV2SplitPairs && (MODE != MODE_C2C);
             constexpr int nE = G::lines_early, nL = G::nlines - G::lines_early;
+            static_assert(!SPLIT || (nE == TX && nL == TX), "real modes: one zone per member of the line pairs");
             const int nl = which ? nL : nE;
             const int lbase = which ? nE : 0;
             const int np = (MODE == MODE_R2C) ? 1 : g.in.np;
             const int limit = (MODE == MODE_C2C) ? g.na : g.na_real; // input lines along a
-            constexpr int lmul = (MODE == MODE_C2C) ? 1 : 2;          // input lines per complex line of the tile
             if (tid == 0) {
                unsigned lines = 0;
                for (int l = 0; l < LY; l++) {
                   const int tile = grp * LY + l;
                   if (tile >= ntiles) break;
-                  const int first = lmul * ((tile % tiles_a) * TX) + lbase;
-                  const int cnt = limit - first;
+                  int cnt;
+                  if constexpr (SPLIT) cnt = (limit - 2 * ((tile % tiles_a) * TX) + (which ? 0 : 1)) / 2; // lines 2 (a0 + q) + which < limit
+                  else cnt = limit - (((MODE == MODE_C2C) ? 1 : 2) * ((tile % tiles_a) * TX) + lbase);
                   lines += (unsigned)(cnt < 0 ? 0 : cnt > nl ? nl : cnt);
                }
                mbar_expect_tx(mb, lines * (unsigned)(G::line_elems * G::line_esize));
@@ -325,7 +346,8 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                const int tile = grp * LY + l;
                if (tile >= ntiles) continue;
                const int b = tile / tiles_a;
-               const int aline = lmul * ((tile - b * tiles_a) * TX) + lbase + q;
+               constexpr int lmul = (MODE == MODE_C2C) ? 1 : 2; // input lines per complex line of the tile
+               const int aline = SPLIT ? 2 * ((tile - b * tiles_a) * TX + q) + which : lmul * ((tile - b * tiles_a) * TX) + lbase + q;
                if (aline >= limit) continue;
                unsigned char *dst = (which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub)) + (size_t)q * G::line_pitch;
                if constexpr (MODE == MODE_R2C) {
@@ -373,11 +395,16 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             } else if constexpr (MODE == MODE_C2C) {
                const unsigned char *line = (tx < G::lines_early) ? Lmine + (size_t)tx * G::line_pitch : Xmine + (size_t)(tx - G::lines_early) * G::line_pitch;
                x = reinterpret_cast<const T2 *>(line)[row];
-            } else { // R2C from two real lines
-               const int l0 = 2 * tx;
-               const unsigned char *la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
-               x.x = reinterpret_cast<const T *>(la)[row];
-               x.y = reinterpret_cast<const T *>(la + G::line_pitch)[row];
+            } else { // R2C from two real lines: even line in the early zone, odd line in the late zone
+               if constexpr (kV2SplitPairs) {
+                  x.x = reinterpret_cast<const T *>(Lmine + (size_t)tx * G::line_pitch)[row];
+                  x.y = reinterpret_cast<const T *>(Xmine + (size_t)tx * G::line_pitch)[row];
+               } else {
+                  const int l0 = 2 * tx;
+                  const unsigned char *la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+                  x.x = reinterpret_cast<const T *>(la)[row];
+                  x.y = reinterpret_cast<const T *>(la + G::line_pitch)[row];
+               }
             }
             if constexpr (MODE == MODE_C2C) x.y = flip_sign(x.y, conj_mask);
             else if (!v1) x.y = 0;
@@ -385,10 +412,16 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             v[s] = x;
          }
       } else { // C2R: Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]); the forward passes get conj(Z)
-         const unsigned char *la = nullptr;
+         const unsigned char *la = nullptr, *lb = nullptr; // half-lines of the pair: A in the early zone, B in the late zone
          if constexpr (INL == IN_LINE) {
-            const int l0 = 2 * tx;
-            la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+            if constexpr (kV2SplitPairs) {
+               la = Lmine + (size_t)tx * G::line_pitch;
+               lb = Xmine + (size_t)tx * G::line_pitch;
+            } else {
+               const int l0 = 2 * tx;
+               la = (l0 < G::lines_early) ? Lmine + (size_t)l0 * G::line_pitch : Xmine + (size_t)(l0 - G::lines_early) * G::line_pitch;
+               lb = la + G::line_pitch;
+            }
          }
 #pragma unroll
          for (int s = 0; s < E; s++) {
@@ -403,7 +436,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                B = reinterpret_cast<const T2 *>(src)[2 * tx + 1];
             } else {
                A = reinterpret_cast<const T2 *>(la)[k];
-               B = reinterpret_cast<const T2 *>(la + G::line_pitch)[k];
+               B = reinterpret_cast<const T2 *>(lb)[k];
             }
             if (!v1) B = T2{0, 0};
             if (TPL * s == 0 || TPL * s == N / 2) { // only these slots can hold bin 0 / bin n/2 (thread j = 0)
@@ -424,7 +457,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
       // ------------------------------------------------------------------ transform
       bool late_done = false;
       if (!g.passthrough) {
-         if constexpr (MODE == MODE_R2C) {
+         if constexpr (MODE == MODE_R2C && !G::mirror_fits) {
             auto nolate = [&]() {};
             RunPasses2<T, P, 0, SP, PADK, decltype(nolate)>::run(v, j, lsm, tws, nolate);
          } else {
@@ -479,19 +512,34 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                }
             }
          }
-      } else { // R2C: separate the two spectra through the exchange buffer, then free it
-         __syncthreads();
-#pragma unroll
-         for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * SP] = v[s];
-         __syncthreads();
+      } else { // R2C: separate the two spectra; partner of bin k is Z[n-k]
          T2 zn[E / 2 + 1];
+         if constexpr (G::mirror_fits) {
+            // slots s >= E/2 hold positions >= n/2; they go to mirror index (position - n/2) in the tail of X
+            if (!late_done) late();
+            T2 *mir = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub + G::mir_off) + tx;
 #pragma unroll
-         for (int s = 0; s <= E / 2; s++) {
-            const int k = j + TPL * s;
-            zn[s] = T2{0, 0};
-            if (k <= N / 2 && (s < E / 2 || j == 0)) zn[s] = lsm[padix<PADK>((N - k) % N) * SP];
+            for (int s = E / 2; s < E; s++) mir[padix<PADK>(j + TPL * (s - E / 2)) * SP] = v[s];
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s <= E / 2; s++) {
+               const int k = j + TPL * s;
+               zn[s] = v[0]; // k == 0 (thread j = 0, slot 0): its own partner
+               if (k > 0 && k <= N / 2 && (s < E / 2 || j == 0)) zn[s] = mir[padix<PADK>(N / 2 - k) * SP]; // Z[n-k] sits at mirror index (n - k) - n/2
+            }
+         } else {
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < E; s++) lsm[padix<PADK>(j + TPL * s) * SP] = v[s];
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s <= E / 2; s++) {
+               const int k = j + TPL * s;
+               zn[s] = T2{0, 0};
+               if (k <= N / 2 && (s < E / 2 || j == 0)) zn[s] = lsm[padix<PADK>((N - k) % N) * SP];
+            }
+            late();
          }
-         late();
          if (!(g.debug & 1) && valid) {
             PieceCursor<T2> cur(g.out, 2 * a, b);
 #pragma unroll

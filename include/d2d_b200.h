@@ -56,6 +56,9 @@ int d2d_ctx_create(d2d_ctx **ctx, const unsigned char id[128], int nranks, int r
  * GPU) and for single-process multi-GPU drivers. */
 int d2d_group_create(d2d_group **grp, int nranks);
 int d2d_group_destroy(d2d_group *grp);
+/* a rank of the group failed: every rank blocked in (or later entering) an exchange of this group returns an error instead
+ * of waiting for it -- the in-process analogue of decomp_2d_abort -> MPI_ABORT (src/decomp_2d_mpi.f90:166-191) */
+int d2d_group_abort(d2d_group *grp);
 int d2d_ctx_create_in_group(d2d_ctx **ctx, d2d_group *grp, int rank, int p_row, int p_col, int device);
 int d2d_ctx_destroy(d2d_ctx *ctx);
 int d2d_ctx_sync(d2d_ctx *ctx);                    /* cudaStreamSynchronize of the context's streams */

@@ -234,3 +234,25 @@ def test_module_level_api_and_host_arrays():
     eng.fft_3d_c2r_host(out_h.ctypes.data, back_h.ctypes.data)
     assert np.max(np.abs(back_h / np.prod(shape) - g)) < 1e-13
     p.decomp_2d_finalize()
+
+
+def test_rank_failure_aborts_the_group_instead_of_hanging():
+    """One rank fails before an exchange: the ranks waiting for it get an error (d2d_group_abort), like
+    decomp_2d_abort -> MPI_ABORT takes the whole job down in the reference (src/decomp_2d_mpi.f90:166-191)."""
+    import time
+    import torch
+    p = pkg()
+    shape, grid = (16, 16, 16), (2, 2)
+
+    def body(rank, group):
+        d2d = p.Decomp2d(*shape, grid[0], grid[1], rank=rank, nranks=4, group=group, device=0)
+        if rank == 3:
+            raise RuntimeError("injected failure on rank 3")
+        u1, u2 = d2d.alloc_x(torch.float64), d2d.alloc_y(torch.float64)
+        d2d.transpose_x_to_y(u1, u2)  # ranks 1 (same column as 3) waits for rank 3 in the exchange
+        return True
+
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="injected failure"):
+        run_ranks(4, body, timeout=60)
+    assert time.monotonic() - t0 < 30
