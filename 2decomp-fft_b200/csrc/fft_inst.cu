@@ -35,7 +35,8 @@ constexpr int TX_WIDE = cmax(1, cmin(2 * TX_WANT, cmin(1024 / P::T, (200 * 1024)
 constexpr int LY_WIDE = cmax(1, cmin(kTargetThreads / (TX_WIDE * P::T), kMaxSmem / (kLineBytes * TX_WIDE)));
 constexpr int PADK = P::R0; // one padding element per first-pass butterfly (bank-conflict model: tools/smem_conflicts.py)
 
-constexpr int minb_for(int threads) { return cmax(1, (D2D_F64 ? 512 : 768) / threads); }
+// resident blocks per SM the v1 kernels are compiled for; 32-element plans need the whole register file of one block
+constexpr int minb_for(int threads) { return P::E >= 32 ? (D2D_F64 ? 1 : 2) : cmax(1, (D2D_F64 ? 512 : 768) / threads); }
 
 template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
    using G = KernelGeom<real_t, P, TX, LY, PADK, LM>;

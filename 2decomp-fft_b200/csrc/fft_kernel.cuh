@@ -233,15 +233,19 @@ D2D_PLAN(32, 8, 8, 4, 1, 1)
 D2D_PLAN(64, 8, 8, 8, 1, 1)
 D2D_PLAN(128, 16, 16, 8, 1, 1)
 D2D_PLAN(256, 16, 16, 16, 1, 1)
-#ifdef D2D_PLAN1024_R32
-D2D_PLAN(512, 32, 32, 16, 1, 1)
-#else
+// 512 and 1024: two passes = ONE shared-memory exchange per transform (32 elements per thread).  Measured on B200,
+// 1024^3 fp64: c2c stages 2.9-3.0 ms (87-91 % of the measured HBM copy rate) against 3.1-3.6 ms with the three-pass
+// plans 8.8.8 / 16.16.4 (make VARIANT=_r16 EXTRA=-DD2D_PLAN_R16 builds those for A/B runs): the kernels were bound by
+// the shared-memory pipe (l1tex 63-74 % busy), and the second exchange was 40 % of its traffic.
+#ifdef D2D_PLAN_R16
 D2D_PLAN(512, 8, 8, 8, 8, 1)
-#endif
-#ifdef D2D_PLAN1024_R32
-D2D_PLAN(1024, 32, 32, 32, 1, 1) // two passes, ONE shared-memory exchange (experiment: halves the exchange traffic)
 #else
+D2D_PLAN(512, 32, 32, 16, 1, 1)
+#endif
+#ifdef D2D_PLAN_R16
 D2D_PLAN(1024, 16, 16, 16, 4, 1)
+#else
+D2D_PLAN(1024, 32, 32, 32, 1, 1)
 #endif
 D2D_PLAN(2048, 16, 16, 16, 8, 1)
 D2D_PLAN(4096, 16, 16, 16, 16, 1)

@@ -110,7 +110,7 @@ struct StageDef {
 // buffer.  Three work buffers rotate; a single-rank complex-output transform borrows `out` as the
 // first one.
 static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward);
-static size_t uniform_work_bytes(const Plan &p);
+static size_t uniform_work_bytes(const Plan &p, bool c2c);
 
 static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
@@ -118,7 +118,7 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
    if (p2p_active(ctx)) return run_chain_p2p(p, dc, dr, st, in, out, backward);
    const int es = p.f64 ? 16 : 8;
    const int padq = 128 / es;
-   const size_t wbytes = uniform_work_bytes(p);
+   const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
    // `out` can stand in for the first work buffer only when the padded wire layout fits in it
    const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C && wbytes <= (size_t)es * dc.pencil_elems(st[2].pencil);
    int live_a = -1, live_b = -1; // work buffers holding the current stage's input
@@ -164,15 +164,20 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
 
 // work-buffer size (bytes) that is the same on every rank of the grid (ragged decompositions give the last
 // ranks bigger pencils): peers address each other's buffers, so all of them must (re)allocate together
-static size_t uniform_work_bytes(const Plan &p)
+//
+// r2c / c2r chains move complex pencils of `sp`, c2c chains complex pencils of `ph` (about twice as large).  The reference
+// sizes its work buffers for the largest complex pencil of any decomposition seen (src/decomp_2d.f90:461-485), so an
+// r2c-only user pays for c2c buffers; here the c2c size is reserved by the first c2c call instead (2048^3 fp32 r2c on one
+// B200: 2 x 34 GB instead of 2 x 69 GB of work space).
+static size_t uniform_work_bytes(const Plan &p, bool c2c)
 {
    const int es = p.f64 ? 16 : 8;
+   const Decomp &g = c2c ? p.ph.d : p.sp.d;
    int64_t m = 0;
    for (int r = 0; r < p.ctx->nranks; r++) {
-      Decomp a, b;
-      decomp_init(a, p.sp.d.nx, p.sp.d.ny, p.sp.d.nz, p.ctx->p_row, p.ctx->p_col, r);
-      decomp_init(b, p.ph.d.nx, p.ph.d.ny, p.ph.d.nz, p.ctx->p_row, p.ctx->p_col, r);
-      m = std::max(m, std::max(fft_work_elems(a, 128 / es), fft_work_elems(b, 128 / es)));
+      Decomp a;
+      decomp_init(a, g.nx, g.ny, g.nz, p.ctx->p_row, p.ctx->p_col, r);
+      m = std::max(m, fft_work_elems(a, 128 / es));
    }
    return (size_t)es * (size_t)m;
 }
@@ -273,15 +278,19 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
    }
 }
 
-static void reserve_all(Plan &p)
+// Grow the context's work buffers to what a chain of this kind needs.  Collective when it grows (every rank computes the
+// same size and has the same history of sizes, so all ranks take the same branch): peers map each other's buffers.
+// Called at plan creation for the r2c / c2r size and by the first c2c call for the c2c size -- never inside a steady loop.
+static void ensure_work(Plan &p, bool c2c, bool at_plan_creation)
 {
-   // grow the context's work buffers once, at plan time (never inside the timed path)
-   const size_t wb = uniform_work_bytes(p);
-   const bool multi = p.ctx->nranks > 1;
-   p.ctx->reserve(0, wb);
-   p.ctx->reserve(1, wb);
-   if (multi) p.ctx->reserve(2, wb);
-   p2p_publish(p.ctx); // collective (no-op for a single rank / in-process groups)
+   Ctx *ctx = p.ctx;
+   const size_t wb = uniform_work_bytes(p, c2c);
+   const int nbuf = ctx->nranks > 1 ? 3 : 2;
+   bool grow = false;
+   for (int i = 0; i < nbuf; i++) grow = grow || ctx->work_bytes[i] < wb;
+   if (!grow && !at_plan_creation) return;
+   for (int i = 0; i < nbuf; i++) ctx->reserve(i, wb);
+   p2p_publish(ctx); // collective (no-op for a single rank / in-process groups)
 }
 
 Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])
@@ -299,7 +308,7 @@ Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int i
    if (format == D2D_PHYSICAL_IN_X) decomp_init(p->sp.d, nx / 2 + 1, ny, nz, ctx->p_row, ctx->p_col, ctx->rank);
    else decomp_init(p->sp.d, nx, ny, nz / 2 + 1, ctx->p_row, ctx->p_col, ctx->rank);
    D2D_CHECK_CUDA(cudaSetDevice(ctx->device));
-   reserve_all(*p);
+   ensure_work(*p, false, true);
    return p.release();
 }
 
@@ -321,6 +330,7 @@ void fft_3d_c2c(Plan *p, void *in, void *out, int isign)
 {
    D2D_REQUIRE(isign == D2D_FFT_FORWARD || isign == D2D_FFT_BACKWARD, "isign must be -1 or +1");
    D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+   ensure_work(*p, true, false); // first c2c call of this context: grows the work buffers to the ph-complex size (collective)
    ProfScope ps(p->ctx, "fft_c2c");
    const bool xyz = (p->format == D2D_PHYSICAL_IN_X && isign == D2D_FFT_FORWARD) ||
                     (p->format == D2D_PHYSICAL_IN_Z && isign == D2D_FFT_BACKWARD);

@@ -32,6 +32,21 @@ def _relerr(a, b):
     return np.max(np.abs(a - b)) / np.max(np.abs(b))
 
 
+def _max_prime(n):
+    m, f = 1, 2
+    while f * f <= n:
+        while n % f == 0:
+            m, n = max(m, f), n // f
+        f += 1
+    return max(m, n) if n > 1 else m
+
+
+# The Glassman oracle advances its twiddles by recurrence (src/glassman.f90:103): for a prime factor p its own distance to
+# the exact DFT grows with p (measured here: 4e-13 at p = 127, 1.0e-12 at 257, 2e-11 at 1021).  Lengths with a larger prime
+# factor are therefore pinned against the exact DFT (numpy's pocketfft = what the reference's FFTW build computes) only.
+ORACLE_MAX_PRIME = 127
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("axis", [0, 1, 2])
 @pytest.mark.parametrize("n", LENGTHS)
@@ -48,10 +63,13 @@ def test_c2c_1m_any_length(n, axis, prec):
         t.copy_(torch.from_numpy(a))
         out = _falloc(torch, shape, cdt)
         d2d.c2c_1m(t, axis, isign, out=out)
-        ref = orc.c2c_1m(a, axis, isign)
-        assert _relerr(out.cpu().numpy(), ref) < TOL[prec], (n, axis, isign)
+        exact = np.fft.fft(a, axis=axis) if isign == -1 else np.fft.ifft(a, axis=axis) * n
+        assert _relerr(out.cpu().numpy(), exact) < TOL[prec], (n, axis, isign)
+        if _max_prime(n) <= ORACLE_MAX_PRIME:
+            ref = orc.c2c_1m(a, axis, isign)
+            assert _relerr(out.cpu().numpy(), ref) < TOL[prec], (n, axis, isign)
         d2d.c2c_1m(t, axis, isign)  # in place
-        assert _relerr(t.cpu().numpy(), ref) < TOL[prec]
+        assert _relerr(t.cpu().numpy(), exact) < TOL[prec]
     d2d.finalize()
 
 
@@ -74,14 +92,16 @@ def test_r2c_c2r_1m_any_length(n, batch, axis, prec):
     t.copy_(torch.from_numpy(a))
     out = _falloc(torch, cshape, cdt)
     d2d.r2c_1m(t, out, axis)
-    ref = orc.r2c_1m(a, axis)
+    use_oracle = _max_prime(n) <= ORACLE_MAX_PRIME
+    ref = orc.r2c_1m(a, axis) if use_oracle else np.fft.rfft(a, axis=axis)
     assert _relerr(out.cpu().numpy(), ref) < TOL[prec]
     spec = np.asfortranarray(rng.uniform(-1, 1, cshape) + 1j * rng.uniform(-1, 1, cshape))
     tc = _falloc(torch, cshape, cdt)
     tc.copy_(torch.from_numpy(spec))
     back = _falloc(torch, shape, rdt)
     d2d.c2r_1m(tc, back, axis)
-    ref_r = orc.c2r_1m(spec, n, axis)
+    # numpy's irfft drops Im(bin 0) / Im(bin n/2) exactly like the reference's "real part of a c2c"
+    ref_r = orc.c2r_1m(spec, n, axis) if use_oracle else np.fft.irfft(spec, n=n, axis=axis) * n
     assert _relerr(back.cpu().numpy(), ref_r) < TOL[prec]
     d2d.finalize()
 
