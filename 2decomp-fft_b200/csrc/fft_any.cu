@@ -89,7 +89,7 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
    if (e != cudaSuccess) return e;
    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
    const long long total = (long long)ga.a.na * ga.a.nb;
-   const long long groups = (total + ga.lines - 1) / ga.lines;
+   const long long groups = (total + (1 << ga.lines_log2) - 1) >> ga.lines_log2;
    if (groups <= 0) return cudaSuccess;
    const long long resident = (long long)sms * per_sm;
    const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
@@ -98,7 +98,8 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
 }
 } // namespace
 
-// factors of n in pass order: 4s, then a 2, then the odd primes in increasing order
+// factors of n in pass order: primes above kAnyMaxFixedOdd first (the first of them needs no twiddles), then 16s and the
+// remaining power of two, then 9s, 3s, 5s, 7s, 11s, 13s
 int fft_any_factorize(int n, int *radix, int maxp)
 {
    int np = 0;
@@ -106,11 +107,20 @@ int fft_any_factorize(int n, int *radix, int maxp)
       if (np < maxp) radix[np] = r;
       np++;
    };
-   while (n % 4 == 0) { push(4); n /= 4; }
-   if (n % 2 == 0) { push(2); n /= 2; }
-   for (int f = 3; (long long)f * f <= n; f += 2)
-      while (n % f == 0) { push(f); n /= f; }
-   if (n > 1) push(n);
+   int small = 1; // product of the factors with register butterflies
+   int m = n;
+   for (int f = 2; f <= kAnyMaxFixedOdd; f++)
+      while (m % f == 0) { m /= f; small *= f; }
+   for (int f = kAnyMaxFixedOdd + 2; (long long)f * f <= m; f += 2)
+      while (m % f == 0) { push(f); m /= f; }
+   if (m > 1) push(m);
+   while (small % 16 == 0) { push(16); small /= 16; }
+   if (small % 8 == 0) { push(8); small /= 8; }
+   if (small % 4 == 0) { push(4); small /= 4; }
+   if (small % 2 == 0) { push(2); small /= 2; }
+   while (small % 9 == 0) { push(9); small /= 9; }
+   for (int f = 3; f <= kAnyMaxFixedOdd; f += 2)
+      while (small % f == 0) { push(f); small /= f; }
    return np;
 }
 
@@ -142,14 +152,18 @@ cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
    else ga.in_fast_a = (g.in.sa[0] == 1 && g.in.se[0] != 1);
    if (mode == MODE_C2R) ga.out_fast_a = (g.rsa == 1 && g.rse != 1);
    else ga.out_fast_a = (g.out.sa[0] == 1 && g.out.se[0] != 1);
-   // lines per block: 128-byte rows when lines are strided, and enough elements to keep 256 threads busy
-   const int want_rows = (int)(128 / ces);
-   int lines = std::max(want_rows, (2048 + n - 1) / n);
-   const long long max_lines = ((long long)(kAnySmemBudget / ces) - n) / (2LL * ga.pitch);
-   lines = (int)std::min<long long>(lines, std::max<long long>(1, max_lines));
-   lines = (int)std::min<long long>(lines, std::max<long long>(1, (long long)g.na * g.nb));
-   ga.lines = lines;
-   const size_t smem = ces * ((size_t)n + 2 * (size_t)lines * ga.pitch);
+   // lines per block (a power of two): 128-byte rows when lines are strided, about 2048 elements of work per block,
+   // within the shared-memory budget; narrower (never below the row width) when that lets two blocks share an SM
+   auto smem_of = [&](int lines) { return ces * ((size_t)n + 2 * (size_t)lines * ga.pitch); };
+   auto pow2_ceil = [](long long v) { int l = 0; while ((1LL << l) < v) l++; return l; };
+   const int want_rows_log2 = pow2_ceil((long long)(128 / ces));
+   int ll = std::max(want_rows_log2, pow2_ceil((2048 + n - 1) / n));
+   ll = std::min(ll, pow2_ceil(kAnyMaxLines));
+   ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
+   while (ll > 0 && smem_of(1 << ll) > kAnySmemBudget) ll--;
+   while (ll > want_rows_log2 && smem_of(1 << ll) > 100 * 1024) ll--;
+   ga.lines_log2 = ll;
+   const size_t smem = smem_of(1 << ll);
    if (mode == MODE_C2C) return f64 ? launch_any<double, MODE_C2C>(ga, smem, ctx->stream) : launch_any<float, MODE_C2C>(ga, smem, ctx->stream);
    if (mode == MODE_R2C) return f64 ? launch_any<double, MODE_R2C>(ga, smem, ctx->stream) : launch_any<float, MODE_R2C>(ga, smem, ctx->stream);
    return f64 ? launch_any<double, MODE_C2R>(ga, smem, ctx->stream) : launch_any<float, MODE_C2R>(ga, smem, ctx->stream);

@@ -8,205 +8,283 @@
 // mem_split_* / mem_merge_* of src/transpose_*.f90 through the piece maps.
 //
 // Algorithm: mixed-radix Stockham autosort between two shared-memory buffers, one pass per factor of n.
-// Factors 2, 3, 4, 5, 7 have register butterflies; any other prime factor R is a direct R-point DFT
-// (one output element per work item, R terms) -- the same O(n * sum of factors) work as the reference's
-// Glassman routine.  All twiddles and DFT coefficients are n-th roots of unity, so ONE table
-// W[k] = exp(-2 pi i k / n) (computed in extended precision on the host) staged in shared memory serves
-// every pass.  A block owns `lines` adjacent lines; lanes run along whichever axis is unit-stride in
-// global memory on the load side and on the store side (independently), so strided pencils are read and
-// written in lines * sizeof(complex) contiguous runs.
+//   * factors 16, 8, 4, 2: the register butterflies of the power-of-two kernels;
+//   * odd factors 3..13: register DFT using the conjugate symmetry of the coefficients (inputs r and R-r are
+//     combined first, outputs k and R-k come out of the same two real-weighted sums: half the multiplies);
+//   * any larger prime R: direct R-point DFT from shared memory with the same pairing, one pair of outputs
+//     (k, R-k) per work item -- O(n * sum of factors) work like the reference's Glassman routine, which
+//     is what keeps e.g. n = 17 * 2^k usable.  These passes run FIRST (no twiddles when nothing precedes them);
+//     a second large prime gets its twiddles applied in a separate in-place sweep.
+// All twiddles and DFT coefficients are n-th roots of unity, so ONE table W[k] = exp(-2 pi i k / n)
+// (computed in extended precision on the host) staged in shared memory serves every pass.
+// A block owns 2^lines_log2 adjacent lines; lanes run along whichever axis is unit-stride in global memory
+// on the load side and on the store side (independently), so strided pencils are read and written in
+// lines * sizeof(complex) contiguous runs.  No integer division in the inner loops (power-of-two line
+// counts, warp-per-line walks, float-reciprocal quotients for the pass indices).
 //
 // Real transforms: two-for-one like the other kernels (two real lines = one complex line), valid for odd n
 // as well: bins 0..floor(n/2) are produced / consumed, Im(bin 0) and (even n) Im(bin n/2) are ignored by c2r.
 #pragma once
 #include "fft_kernel.cuh"
 
-#if defined(__CUDACC__)
-#define D2D_HD __host__ __device__ __forceinline__
-#else
-#define D2D_HD inline
-#endif
-
 namespace d2d {
 
 constexpr int kMaxAnyPass = 32;
 constexpr int kAnyThreads = 256;
+constexpr int kAnyMaxLines = 256;    // lines per block (power of two; 256 = one thread per line)
+constexpr int kAnyMaxFixedOdd = 13;  // largest odd radix with a register butterfly
 
 struct FftArgsAny {
    FftArgs a;                 // a.tw = W[k] = exp(-2 pi i k / n), k in [0, n)
    int npass;
    int radix[kMaxAnyPass];
-   int lines;                 // complex lines per block
+   int lines_log2;            // complex lines per block = 1 << lines_log2
    int pitch;                 // shared-memory pitch of a line, in complex elements (odd)
    int in_fast_a, out_fast_a; // 1: adjacent lines (axis a) are contiguous in global memory on that side
 };
 
-template <typename T2> D2D_HD T2 any_cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
-template <typename T2> D2D_HD T2 any_csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
-template <typename T2> D2D_HD T2 any_cmul(T2 a, T2 b) { return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-template <typename T2> D2D_HD T2 any_mul_mi(T2 a) { return T2{a.y, -a.x}; }
+// floor(x / d) for 0 <= x < 2^22, d >= 1, rd = 1.0f / d: (x + 0.5) / d is at least 0.5 / d away from an integer, far
+// more than the rounding error of the float product
+D2D_HD int any_div(int x, int d, float rd)
+{
+#if defined(__CUDA_ARCH__)
+   return __float2int_rd(((float)x + 0.5f) * rd);
+#else
+   (void)rd;
+   return x / d;
+#endif
+}
 
 // Stockham pass (R, Ns) of an n-point transform, n = M R:
 //   butterfly jj in [0, M): inputs src[jj + r M], r in [0, R), twiddled by exp(-2 pi i q r / (Ns R)), q = jj % Ns;
 //   outputs dst[(jj / Ns) Ns R + q + k Ns], k in [0, R).
 // Register butterfly for a compile-time radix.
-template <typename T2, int R> D2D_HD void any_bfly_fixed(const T2 *src, T2 *dst, const T2 *W, int n, int Ns, int jj)
+template <typename T, int R> D2D_HD void any_bfly_fixed(const typename Vec2<T>::type *src, typename Vec2<T>::type *dst,
+                                                          const typename Vec2<T>::type *W, int n, int Ns, float rNs, int jj)
 {
+   using T2 = typename Vec2<T>::type;
    const int M = n / R;
-   const int q = jj % Ns;
+   const int q = jj - any_div(jj, Ns, rNs) * Ns;
    const int base = (jj - q) * R + q;
    const int s = n / (Ns * R); // exp(-2 pi i q r / (Ns R)) = W[q r s], and q r s < n
    T2 x[R];
    x[0] = src[jj];
+   if (Ns == 1) {
 #pragma unroll
-   for (int r = 1; r < R; r++) x[r] = any_cmul(src[jj + r * M], W[q * s * r]);
-   if constexpr (R == 2) {
-      dst[base] = any_cadd(x[0], x[1]);
-      dst[base + Ns] = any_csub(x[0], x[1]);
-   } else if constexpr (R == 4) {
-      const T2 a0 = any_cadd(x[0], x[2]), a1 = any_csub(x[0], x[2]);
-      const T2 a2 = any_cadd(x[1], x[3]), a3 = any_mul_mi(any_csub(x[1], x[3]));
-      dst[base] = any_cadd(a0, a2);
-      dst[base + Ns] = any_cadd(a1, a3);
-      dst[base + 2 * Ns] = any_csub(a0, a2);
-      dst[base + 3 * Ns] = any_csub(a1, a3);
+      for (int r = 1; r < R; r++) x[r] = src[jj + r * M];
    } else {
-      // direct R-point DFT in registers: X[k] = sum_r x[r] W[(r k mod R) M]
+      const int qs = q * s;
 #pragma unroll
-      for (int k = 0; k < R; k++) {
-         T2 acc = x[0];
+      for (int r = 1; r < R; r++) x[r] = cmul(src[jj + r * M], W[qs * r]);
+   }
+   if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
+      Bfly<T, R>::template run<0, 1>(x);
 #pragma unroll
-         for (int r = 1; r < R; r++) acc = any_cadd(acc, any_cmul(x[r], W[((r * k) % R) * M]));
-         dst[base + k * Ns] = acc;
+      for (int k = 0; k < R; k++) dst[base + k * Ns] = x[Bfly<T, R>::out_idx(k)];
+   } else {
+      // odd R: with sr = x[r] + x[R-r], dr = x[r] - x[R-r], w^m = (c_m, -s_m):
+      //   X[k], X[R-k] = (x0 + sum_r c_{rk} sr)  -/+  i (sum_r s_{rk} dr),  r = 1..(R-1)/2
+      static_assert(R % 2 == 1, "odd radix expected");
+      constexpr int H = (R - 1) / 2;
+      T wc[H + 1], ws[H + 1]; // c_m, s_m for m = 0..H (c_{R-m} = c_m, s_{R-m} = -s_m)
+      wc[0] = (T)1; // m = r k mod R is 0 only for composite R (9)
+      ws[0] = (T)0;
+#pragma unroll
+      for (int m = 1; m <= H; m++) {
+         const T2 w = W[m * M];
+         wc[m] = w.x;
+         ws[m] = -w.y;
+      }
+      T2 sum = x[0];
+#pragma unroll
+      for (int r = 1; r <= H; r++) {
+         const T2 a = x[r], b = x[R - r];
+         x[r] = cadd(a, b);
+         x[R - r] = csub(a, b);
+         sum = cadd(sum, x[r]);
+      }
+      dst[base] = sum;
+#pragma unroll
+      for (int k = 1; k <= H; k++) {
+         T2 p = x[0], qq = T2{0, 0};
+#pragma unroll
+         for (int r = 1; r <= H; r++) {
+            const int m = (r * k) % R;
+            const T c = m <= H ? wc[m] : wc[R - m];
+            const T sn = m <= H ? ws[m] : -ws[R - m];
+            p.x += c * x[r].x;
+            p.y += c * x[r].y;
+            qq.x += sn * x[R - r].x;
+            qq.y += sn * x[R - r].y;
+         }
+         dst[base + k * Ns] = T2{p.x + qq.y, p.y - qq.x};       // P - i Q
+         dst[base + (R - k) * Ns] = T2{p.x - qq.y, p.y + qq.x}; // P + i Q
       }
    }
 }
 
-// One OUTPUT element o in [0, n) of pass (R, Ns) for a run-time radix R (any prime):
-//   o = g Ns R + k Ns + q  ->  sum_r src[g Ns + q + r M] W[r (q s + k M) mod n]
-template <typename T2> D2D_HD T2 any_out_runtime(const T2 *src, const T2 *W, int n, int R, int Ns, int o)
+// Large prime radix R (run time): work item (butterfly jj, kp in [0, (R-1)/2]) produces X[kp] and X[R-kp] of that
+// butterfly from inputs that already carry their twiddles.
+template <typename T> D2D_HD void any_pair_runtime(const typename Vec2<T>::type *src, typename Vec2<T>::type *dst,
+                                                    const typename Vec2<T>::type *W, int n, int R, int Ns, float rNs, int jj, int kp)
 {
-   const int M = n / R;
-   const int q = o % Ns;
-   const int k = (o / Ns) % R;
-   const int gq = (o / (Ns * R)) * Ns + q; // butterfly index jj
-   const int s = n / (Ns * R);
-   const int step = q * s + k * M; // < n
-   T2 acc = src[gq];
+   using T2 = typename Vec2<T>::type;
+   const int M = n / R, H = (R - 1) / 2;
+   const int q = jj - any_div(jj, Ns, rNs) * Ns;
+   const int base = (jj - q) * R + q;
+   T2 p = src[jj], qq = T2{0, 0};
+   const int step = kp * M; // W[r kp M mod n]: coefficient of input r for output kp
    int idx = 0;
-   for (int r = 1; r < R; r++) {
+   for (int r = 1; r <= H; r++) {
       idx += step;
       if (idx >= n) idx -= n;
-      acc = any_cadd(acc, any_cmul(src[gq + r * M], W[idx]));
+      const T2 a = src[jj + r * M], b = src[jj + (R - r) * M];
+      const T2 w = W[idx]; // (c, -s)
+      p.x += w.x * (a.x + b.x);
+      p.y += w.x * (a.y + b.y);
+      qq.x -= w.y * (a.x - b.x);
+      qq.y -= w.y * (a.y - b.y);
    }
-   return acc;
+   if (kp == 0) {
+      dst[base] = p; // all coefficients are 1: p = sum of the inputs, qq = 0
+   } else {
+      dst[base + kp * Ns] = T2{p.x + qq.y, p.y - qq.x};
+      dst[base + (R - kp) * Ns] = T2{p.x - qq.y, p.y + qq.x};
+   }
 }
 
 #if defined(__CUDACC__)
 
-template <typename T2, int R>
-__device__ __forceinline__ void any_pass_fixed(const T2 *src, T2 *dst, const T2 *W, int n, int Ns, int lines, int pitch)
+template <typename T, int R>
+__device__ __forceinline__ void any_pass_fixed(const typename Vec2<T>::type *src, typename Vec2<T>::type *dst, const typename Vec2<T>::type *W,
+                                               int n, int Ns, float rNs, int pt, int TL)
 {
    const int M = n / R;
-   const int items = lines * M;
-   for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-      const int l = i / M, jj = i - l * M;
-      any_bfly_fixed<T2, R>(src + l * pitch, dst + l * pitch, W, n, Ns, jj);
-   }
+   for (int jj = pt; jj < M; jj += TL) any_bfly_fixed<T, R>(src, dst, W, n, Ns, rNs, jj);
 }
 
 template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) fft_any_kernel(const __grid_constant__ FftArgsAny ga)
 {
    using T2 = typename Vec2<T>::type;
    const FftArgs &g = ga.a;
-   const int n = g.n, L = ga.lines, pitch = ga.pitch;
+   const int n = g.n, LL = ga.lines_log2, L = 1 << LL, pitch = ga.pitch;
    const int nh = n / 2 + 1;
    extern __shared__ __align__(16) unsigned char any_smem[];
    T2 *W = reinterpret_cast<T2 *>(any_smem);
    T2 *buf0 = W + n;
    T2 *buf1 = buf0 + (size_t)L * pitch;
+   __shared__ int line_a[kAnyMaxLines], line_b[kAnyMaxLines]; // (a, b) of the block's lines; a = -1: beyond the batch
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   constexpr int NW = kAnyThreads / 32;
+   // pass identity: TL threads per line
+   const int TL = kAnyThreads >> LL;
+   const int pl = tid >> (8 - LL), pt = tid & (TL - 1); // kAnyThreads == 256
+   static_assert(kAnyThreads == 256, "thread indexing assumes 256 threads");
    {
       const T2 *__restrict__ wg = reinterpret_cast<const T2 *>(g.tw);
-      for (int i = threadIdx.x; i < n; i += kAnyThreads) W[i] = ldg_nc(wg + i);
+      for (int i = tid; i < n; i += kAnyThreads) W[i] = ldg_nc(wg + i);
    }
    const long long total = (long long)g.na * g.nb; // complex lines (pairs of real lines for r2c / c2r)
-   const long long ngroups = (total + L - 1) / L;
+   const long long ngroups = (total + L - 1) >> LL;
    const bool bw = g.backward != 0;
+   T2 *const my0 = buf0 + pl * pitch, *const my1 = buf1 + pl * pitch;
 
    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-      __syncthreads(); // W is staged; the previous group's stores have read the buffers
-      const long long id0 = grp * L;
+      __syncthreads(); // W is staged; the previous group's stores have read the buffers and the line table
+      if (tid < L) {
+         const long long id = (grp << LL) + tid;
+         int a = -1, b = 0;
+         if (id < total) {
+            b = (int)(id / g.na);
+            a = (int)(id - (long long)b * g.na);
+         }
+         line_a[tid] = a;
+         line_b[tid] = b;
+      }
+      __syncthreads();
       // ------------------------------------------------------------------ load -> buf0
+      // fast_a: lanes run over the lines first (l = i mod L); otherwise one warp walks along a line
+      auto for_each = [&](int len, bool fast_a, auto &&fn) {
+         if (fast_a) {
+            const int items = len << LL;
+            for (int i = tid; i < items; i += kAnyThreads) fn(i & (L - 1), i >> LL);
+         } else {
+            for (int l = warp; l < L; l += NW)
+               for (int e = lane; e < len; e += 32) fn(l, e);
+         }
+      };
       if constexpr (MODE == MODE_C2C) {
-         const int items = L * n;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, e;
-            if (ga.in_fast_a) { e = i / L; l = i - e * L; }
-            else { l = i / n; e = i - l * n; }
-            const long long id = id0 + l;
+         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            const int a = line_a[l];
             T2 x = T2{0, 0};
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               x = load_piece<T2>(g.in, e, a, b);
+            if (a >= 0) {
+               x = load_piece<T2>(g.in, e, a, line_b[l]);
                if (bw) x.y = -x.y;
             }
             buf0[l * pitch + e] = x;
-         }
+         });
       } else if constexpr (MODE == MODE_R2C) {
          const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
-         const int items = L * n;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, e;
-            if (ga.in_fast_a) { e = i / L; l = i - e * L; }
-            else { l = i / n; e = i - l * n; }
-            const long long id = id0 + l;
+         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            const int a = line_a[l];
             T2 x = T2{0, 0};
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               const long long off = (long long)e * g.rse + (2 * a) * g.rsa + b * g.rsb;
+            if (a >= 0) {
+               const long long off = (long long)e * g.rse + (2LL * a) * g.rsa + (long long)line_b[l] * g.rsb;
                x.x = rp[off];
                if (2 * a + 1 < g.na_real) x.y = rp[off + g.rsa];
             }
             buf0[l * pitch + e] = x;
-         }
+         });
       } else { // C2R: Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]); the forward passes get conj(Z)
-         const int items = L * nh;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, k;
-            if (ga.in_fast_a) { k = i / L; l = i - k * L; }
-            else { l = i / nh; k = i - l * nh; }
-            const long long id = id0 + l;
+         for_each(nh, ga.in_fast_a != 0, [&](int l, int k) {
+            const int a = line_a[l];
             T2 A = T2{0, 0}, B = T2{0, 0};
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               A = load_piece<T2>(g.in, k, 2 * a, b);
-               if (2 * a + 1 < g.na_real) B = load_piece<T2>(g.in, k, 2 * a + 1, b);
+            if (a >= 0) {
+               A = load_piece<T2>(g.in, k, 2LL * a, line_b[l]);
+               if (2 * a + 1 < g.na_real) B = load_piece<T2>(g.in, k, 2LL * a + 1, line_b[l]);
             }
             const bool selfconj = (k == 0) || (2 * k == n);
             if (selfconj) { A.y = 0; B.y = 0; }
             buf0[l * pitch + k] = T2{A.x - B.y, -(A.y + B.x)};
             if (!selfconj) buf0[l * pitch + n - k] = T2{A.x + B.y, A.y - B.x};
-         }
+         });
       }
       __syncthreads();
 
-      // ------------------------------------------------------------------ passes (ping-pong)
-      T2 *src = buf0, *dst = buf1;
+      // ------------------------------------------------------------------ passes (ping-pong), line pl, thread pt of TL
+      T2 *src = my0, *dst = my1;
       if (!g.passthrough) {
          int Ns = 1;
          for (int p = 0; p < ga.npass; p++) {
             const int R = ga.radix[p];
+            const float rNs = 1.0f / (float)Ns;
             switch (R) {
-            case 2: any_pass_fixed<T2, 2>(src, dst, W, n, Ns, L, pitch); break;
-            case 3: any_pass_fixed<T2, 3>(src, dst, W, n, Ns, L, pitch); break;
-            case 4: any_pass_fixed<T2, 4>(src, dst, W, n, Ns, L, pitch); break;
-            case 5: any_pass_fixed<T2, 5>(src, dst, W, n, Ns, L, pitch); break;
-            case 7: any_pass_fixed<T2, 7>(src, dst, W, n, Ns, L, pitch); break;
+            case 2: any_pass_fixed<T, 2>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 3: any_pass_fixed<T, 3>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 4: any_pass_fixed<T, 4>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 5: any_pass_fixed<T, 5>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 7: any_pass_fixed<T, 7>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 8: any_pass_fixed<T, 8>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 9: any_pass_fixed<T, 9>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 11: any_pass_fixed<T, 11>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 13: any_pass_fixed<T, 13>(src, dst, W, n, Ns, rNs, pt, TL); break;
+            case 16: any_pass_fixed<T, 16>(src, dst, W, n, Ns, rNs, pt, TL); break;
             default: {
-               const int items = L * n;
-               for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-                  const int l = i / n, o = i - l * n;
-                  dst[l * pitch + o] = any_out_runtime<T2>(src + l * pitch, W, n, R, Ns, o);
+               const int M = n / R, H = (R - 1) / 2;
+               if (Ns > 1) { // twiddles in place: src[jj + r M] *= W[q r s]
+                  const int s = n / (Ns * R);
+                  for (int i = pt; i < n; i += TL) {
+                     const int r = any_div(i, M, 1.0f / (float)M), jj = i - r * M;
+                     const int q = jj - any_div(jj, Ns, rNs) * Ns;
+                     if (r > 0 && q > 0) src[i] = cmul(src[i], W[q * s * r]);
+                  }
+                  __syncthreads();
+               }
+               const int items = M * (H + 1);
+               const float rM = 1.0f / (float)M;
+               for (int i = pt; i < items; i += TL) {
+                  const int kp = any_div(i, M, rM), jj = i - kp * M;
+                  any_pair_runtime<T>(src, dst, W, n, R, Ns, rNs, jj, kp);
                }
             }
             }
@@ -215,55 +293,41 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
             Ns *= R;
          }
       }
+      T2 *const res = src - pl * pitch; // block view of the buffer holding the result
 
-      // ------------------------------------------------------------------ store from src
+      // ------------------------------------------------------------------ store
       if (g.debug & 1) continue;
       if constexpr (MODE == MODE_C2C) {
-         const int items = L * n;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, e;
-            if (ga.out_fast_a) { e = i / L; l = i - e * L; }
-            else { l = i / n; e = i - l * n; }
-            const long long id = id0 + l;
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               T2 x = src[l * pitch + e];
+         for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
+            const int a = line_a[l];
+            if (a >= 0) {
+               T2 x = res[l * pitch + e];
                if (bw) x.y = -x.y;
-               store_piece<T2>(g.out, e, a, b, x);
+               store_piece<T2>(g.out, e, a, line_b[l], x);
             }
-         }
+         });
       } else if constexpr (MODE == MODE_C2R) {
          T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
-         const int items = L * n;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, e;
-            if (ga.out_fast_a) { e = i / L; l = i - e * L; }
-            else { l = i / n; e = i - l * n; }
-            const long long id = id0 + l;
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               const long long off = (long long)e * g.rse + (2 * a) * g.rsa + b * g.rsb;
-               const T2 x = src[l * pitch + e];
+         for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
+            const int a = line_a[l];
+            if (a >= 0) {
+               const long long off = (long long)e * g.rse + (2LL * a) * g.rsa + (long long)line_b[l] * g.rsb;
+               const T2 x = res[l * pitch + e];
                rp[off] = x.x;
                if (2 * a + 1 < g.na_real) rp[off + g.rsa] = -x.y;
             }
-         }
+         });
       } else { // R2C: A[k] = (Z[k] + conj Z[n-k]) / 2, B[k] = (Z[k] - conj Z[n-k]) / (2i), k in [0, n/2]
-         const int items = L * nh;
-         for (int i = threadIdx.x; i < items; i += kAnyThreads) {
-            int l, k;
-            if (ga.out_fast_a) { k = i / L; l = i - k * L; }
-            else { l = i / nh; k = i - l * nh; }
-            const long long id = id0 + l;
-            if (id < total) {
-               const long long b = id / g.na, a = id - b * g.na;
-               const T2 zk = src[l * pitch + k];
-               const T2 zn = src[l * pitch + (k == 0 ? 0 : n - k)];
+         for_each(nh, ga.out_fast_a != 0, [&](int l, int k) {
+            const int a = line_a[l];
+            if (a >= 0) {
+               const T2 zk = res[l * pitch + k];
+               const T2 zn = res[l * pitch + (k == 0 ? 0 : n - k)];
                const T hf = (T)0.5;
-               store_piece<T2>(g.out, k, 2 * a, b, T2{(zk.x + zn.x) * hf, (zk.y - zn.y) * hf});
-               if (2 * a + 1 < g.na_real) store_piece<T2>(g.out, k, 2 * a + 1, b, T2{(zk.y + zn.y) * hf, (zn.x - zk.x) * hf});
+               store_piece<T2>(g.out, k, 2LL * a, line_b[l], T2{(zk.x + zn.x) * hf, (zk.y - zn.y) * hf});
+               if (2 * a + 1 < g.na_real) store_piece<T2>(g.out, k, 2LL * a + 1, line_b[l], T2{(zk.y + zn.y) * hf, (zn.x - zk.x) * hf});
             }
-         }
+         });
       }
    }
 }

@@ -63,11 +63,14 @@ template <typename T> struct Vec2;
 template <> struct Vec2<float> { using type = float2; };
 template <> struct Vec2<double> { using type = double2; };
 
-template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
-template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
-template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) { return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// arithmetic shared with host-side checks of the pass arithmetic (tools/micro/test_any_host.cu)
+#define D2D_HD __host__ __device__ __forceinline__
+
+template <typename T2> D2D_HD T2 cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
+template <typename T2> D2D_HD T2 csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
+template <typename T2> D2D_HD T2 cmul(T2 a, T2 b) { return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 // multiply by -i : (x,y) -> (y,-x)
-template <typename T2> __device__ __forceinline__ T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }
+template <typename T2> D2D_HD T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }
 
 template <typename T> struct Consts;
 template <> struct Consts<double> {
@@ -86,13 +89,13 @@ template <typename T, int R> struct Bfly;
 
 template <typename T> struct Bfly<T, 1> {
    using T2 = typename Vec2<T>::type;
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *) {}
+   template <int B, int S> static D2D_HD void run(T2 *) {}
    static constexpr int out_idx(int r) { return r; }
 };
 
 template <typename T> struct Bfly<T, 2> {
    using T2 = typename Vec2<T>::type;
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   template <int B, int S> static D2D_HD void run(T2 *v)
    {
       T2 a = v[B], b = v[B + S];
       v[B] = cadd(a, b);
@@ -103,7 +106,7 @@ template <typename T> struct Bfly<T, 2> {
 
 template <typename T> struct Bfly<T, 4> {
    using T2 = typename Vec2<T>::type;
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   template <int B, int S> static D2D_HD void run(T2 *v)
    {
       T2 a0 = cadd(v[B], v[B + 2 * S]), a1 = csub(v[B], v[B + 2 * S]);
       T2 a2 = cadd(v[B + S], v[B + 3 * S]), a3 = mul_mi(csub(v[B + S], v[B + 3 * S]));
@@ -118,7 +121,7 @@ template <typename T> struct Bfly<T, 4> {
 template <typename T> struct Bfly<T, 8> {
    using T2 = typename Vec2<T>::type;
    // DIF split 2 x 4: X[2m] = DFT4(x_k + x_{k+4})[m], X[2m+1] = DFT4((x_k - x_{k+4}) W8^k)[m]
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   template <int B, int S> static D2D_HD void run(T2 *v)
    {
       const T h = Consts<T>::rsqrt2;
 #pragma unroll
@@ -143,7 +146,7 @@ template <typename T> struct Bfly<T, 8> {
 template <typename T> struct Bfly<T, 16> {
    using T2 = typename Vec2<T>::type;
    // 4 x 4: i = k + 4l, r = m + 4n : X[m+4n] = sum_k W4^{kn} W16^{km} [ sum_l x_{k+4l} W4^{lm} ]
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   template <int B, int S> static D2D_HD void run(T2 *v)
    {
       const T h = Consts<T>::rsqrt2, c = Consts<T>::c8, s = Consts<T>::s8;
       Bfly<T, 4>::template run<B, 4 * S>(v); // u_k[m] at v[B + (k + 4m) S]
@@ -184,7 +187,7 @@ template <typename T> struct Bfly<T, 16> {
 template <typename T> struct Bfly<T, 32> {
    using T2 = typename Vec2<T>::type;
    // DIF split 2 x 16: X[2m] = DFT16(x_k + x_{k+16})[m], X[2m+1] = DFT16((x_k - x_{k+16}) W32^k)[m]
-   template <int B, int S> static __device__ __forceinline__ void run(T2 *v)
+   template <int B, int S> static D2D_HD void run(T2 *v)
    {
       // W32^k = (cos(k pi/16), -sin(k pi/16)), k = 1..15
       constexpr T c1 = (T)0.98078528040323044913, s1 = (T)0.19509032201612826785; // pi/16

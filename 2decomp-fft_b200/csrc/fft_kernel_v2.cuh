@@ -61,6 +61,7 @@ struct FftArgs2 {
    int nops;
    int c0_mul;               // dim-0 coordinate of a tile = a0 * c0_mul (scalars per line along dim 0)
    int bytes_early, bytes_late; // per sub-tile
+   int line_bytes;           // IN_LINE: bytes landed per input line (pieces rounded up to 16 bytes)
    LoadOp ops[kMaxLoadOps];
 };
 
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   else cnt = limit - (((MODE == MODE_C2C) ? 1 : 2) * ((tile % tiles_a) * TX) + lbase);
                   lines += (unsigned)(cnt < 0 ? 0 : cnt > nl ? nl : cnt);
                }
-               mbar_expect_tx(mb, lines * (unsigned)(G::line_elems * G::line_esize));
+               mbar_expect_tx(mb, lines * (unsigned)g2.line_bytes);
             }
             __syncwarp();
             const int nop = LY * nl * np;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                } else {
                   const int e0 = g.in.e0[m], e1 = g.in.e0[m + 1];
                   const T2 *src = reinterpret_cast<const T2 *>(g.in.ptr[m]) + (long long)aline * g.in.sa[m] + (long long)b * g.in.sb[m];
-                  bulk_load(dst + (size_t)e0 * sizeof(T2), src, (unsigned)((e1 - e0) * sizeof(T2)), mb);
+                  bulk_load(dst + (size_t)e0 * sizeof(T2), src, (unsigned)(((e1 - e0) * sizeof(T2) + 15) & ~(size_t)15), mb);
                }
             }
          }

@@ -146,9 +146,20 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
          for (int m = 0; m < g.in.np; m++) {
             if (!aligned16(g.in.ptr[m]) || ((g.in.sa[m] * ces) & 15) || ((g.in.sb[m] * ces) & 15)) return false;
             if (((long long)g.in.e0[m] * ces) & 15) return false;
-            if (((long long)(g.in.e0[m + 1] - g.in.e0[m]) * ces) & 15) return false;
+            // bulk copies move multiples of 16 bytes: an odd fp32 piece (n/2+1 = 513 bins) is read one element long,
+            // which is only legal when the line pitch leaves that room (padded wire layouts do, dense user arrays do not)
+            const long long plen = g.in.e0[m + 1] - g.in.e0[m];
+            const long long rlen = (plen * ces + 15) / 16 * 16 / ces;
+            if (rlen != plen) {
+               const long long pitch_a = g.in.sa[m] < 0 ? -g.in.sa[m] : g.in.sa[m], pitch_b = g.in.sb[m] < 0 ? -g.in.sb[m] : g.in.sb[m];
+               const long long lines_a = (mode == MODE_C2R) ? g.na_real : g.na;
+               if ((lines_a > 1 && pitch_a < rlen) || (g.nb > 1 && pitch_b < rlen) || (lines_a <= 1 && g.nb <= 1)) return false;
+               if (m + 1 < g.in.np) return false; // the over-read would land on the next piece's slot in shared memory
+            }
+            a2.line_bytes += (int)(rlen * ces);
          }
       }
+      if (mode == MODE_R2C) a2.line_bytes = N * es;
    } else {
       // ---- tile-like: tensor maps + box list ----------------------------------------------------------
       const int np = (mode == MODE_R2C) ? 1 : g.in.np;

@@ -1,5 +1,6 @@
 // Host-side check of the arbitrary-length pass arithmetic of csrc/fft_any.cuh (the same __host__ __device__
-// functions the kernel runs) against a naive long-double DFT.  Build: nvcc -std=c++17 -O1 -o test_any_host test_any_host.cu
+// functions the kernel runs, driven by the same factorisation) against a naive long-double DFT.
+// Build: nvcc -std=c++17 -O1 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -o test_any_host test_any_host.cu
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -7,66 +8,102 @@
 
 #include "../../2decomp-fft_b200/csrc/fft_any.cuh"
 
-namespace d2d { int fft_any_factorize(int n, int *radix, int maxp); }
-// copy of the factorisation (fft_any.cu) so that this file builds alone
+namespace d2d {
+// the factorisation of fft_any.cu, restated so that this file builds alone
 static int factorize(int n, int *radix, int maxp)
 {
    int np = 0;
    auto push = [&](int r) { if (np < maxp) radix[np] = r; np++; };
-   while (n % 4 == 0) { push(4); n /= 4; }
-   if (n % 2 == 0) { push(2); n /= 2; }
-   for (int f = 3; (long long)f * f <= n; f += 2)
-      while (n % f == 0) { push(f); n /= f; }
-   if (n > 1) push(n);
+   int small = 1, m = n;
+   for (int f = 2; f <= kAnyMaxFixedOdd; f++)
+      while (m % f == 0) { m /= f; small *= f; }
+   for (int f = kAnyMaxFixedOdd + 2; (long long)f * f <= m; f += 2)
+      while (m % f == 0) { push(f); m /= f; }
+   if (m > 1) push(m);
+   while (small % 16 == 0) { push(16); small /= 16; }
+   if (small % 8 == 0) { push(8); small /= 8; }
+   if (small % 4 == 0) { push(4); small /= 4; }
+   if (small % 2 == 0) { push(2); small /= 2; }
+   while (small % 9 == 0) { push(9); small /= 9; }
+   for (int f = 3; f <= kAnyMaxFixedOdd; f += 2)
+      while (small % f == 0) { push(f); small /= f; }
    return np;
+}
+} // namespace d2d
+
+template <typename T> double run(int n)
+{
+   using namespace d2d;
+   using T2 = typename Vec2<T>::type;
+   int radix[kMaxAnyPass];
+   const int np = factorize(n, radix, kMaxAnyPass);
+   std::vector<T2> W(n), a(n), b(n);
+   std::vector<double> xr(n), xi(n);
+   const long double pi2 = 2 * 3.14159265358979323846264338327950288L;
+   for (int k = 0; k < n; k++) W[k] = T2{(T)cosl(pi2 * k / n), (T)-sinl(pi2 * k / n)};
+   srand(n);
+   for (int k = 0; k < n; k++) {
+      a[k] = T2{(T)(rand() / (double)RAND_MAX - 0.5), (T)(rand() / (double)RAND_MAX - 0.5)};
+      xr[k] = a[k].x; xi[k] = a[k].y;
+   }
+   T2 *src = a.data(), *dst = b.data();
+   int Ns = 1;
+   for (int p = 0; p < np; p++) {
+      const int R = radix[p], M = n / R;
+      const float rNs = 1.0f / Ns;
+      bool fixed = true;
+      for (int jj = 0; jj < M && fixed; jj++) {
+         switch (R) {
+         case 2: any_bfly_fixed<T, 2>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 3: any_bfly_fixed<T, 3>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 4: any_bfly_fixed<T, 4>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 5: any_bfly_fixed<T, 5>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 7: any_bfly_fixed<T, 7>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 8: any_bfly_fixed<T, 8>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 9: any_bfly_fixed<T, 9>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 11: any_bfly_fixed<T, 11>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 13: any_bfly_fixed<T, 13>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         case 16: any_bfly_fixed<T, 16>(src, dst, W.data(), n, Ns, rNs, jj); break;
+         default: fixed = false;
+         }
+      }
+      if (!fixed) { // the kernel's run-time radix path: twiddle sweep, then one item per (butterfly, output pair)
+         const int H = (R - 1) / 2;
+         if (Ns > 1) {
+            const int s = n / (Ns * R);
+            for (int i = 0; i < n; i++) {
+               const int r = i / M, jj = i - r * M, q = jj % Ns;
+               if (r > 0 && q > 0) src[i] = cmul(src[i], W[q * s * r]);
+            }
+         }
+         for (int i = 0; i < M * (H + 1); i++) any_pair_runtime<T>(src, dst, W.data(), n, R, Ns, rNs, i % M, i / M);
+      }
+      std::swap(src, dst);
+      Ns *= R;
+   }
+   double err = 0, mx = 0;
+   for (int k = 0; k < n; k++) {
+      long double re = 0, im = 0;
+      for (int j = 0; j < n; j++) {
+         const long double ang = -pi2 * (long double)((long long)j * k % n) / n;
+         re += xr[j] * cosl(ang) - xi[j] * sinl(ang);
+         im += xr[j] * sinl(ang) + xi[j] * cosl(ang);
+      }
+      err = fmax(err, fmax(fabs((double)(src[k].x - re)), fabs((double)(src[k].y - im))));
+      mx = fmax(mx, fmax(fabs((double)re), fabs((double)im)));
+   }
+   printf("n=%5d passes=%d [", n, np);
+   for (int p = 0; p < np; p++) printf("%d%s", radix[p], p + 1 < np ? "." : "");
+   printf("] rel err %.2e\n", err / mx);
+   return err / mx;
 }
 
 int main()
 {
-   using namespace d2d;
-   const int sizes[] = {1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 17, 18, 20, 21, 22, 24, 26, 27, 34, 35, 49, 51, 60, 66, 68, 100, 102, 121, 127, 130, 210, 257, 289, 360, 1000, 1001};
-   double worst = 0;
-   for (int n : sizes) {
-      int radix[kMaxAnyPass];
-      const int np = factorize(n, radix, kMaxAnyPass);
-      std::vector<double2> W(n), a(n), b(n), x(n);
-      const long double pi2 = 2 * 3.14159265358979323846264338327950288L;
-      for (int k = 0; k < n; k++) W[k] = double2{(double)cosl(pi2 * k / n), (double)-sinl(pi2 * k / n)};
-      srand(n);
-      for (int k = 0; k < n; k++) x[k] = a[k] = double2{rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5};
-      double2 *src = a.data(), *dst = b.data();
-      int Ns = 1;
-      for (int p = 0; p < np; p++) {
-         const int R = radix[p], M = n / R;
-         for (int jj = 0; jj < M; jj++) {
-            switch (R) {
-            case 2: any_bfly_fixed<double2, 2>(src, dst, W.data(), n, Ns, jj); break;
-            case 3: any_bfly_fixed<double2, 3>(src, dst, W.data(), n, Ns, jj); break;
-            case 4: any_bfly_fixed<double2, 4>(src, dst, W.data(), n, Ns, jj); break;
-            case 5: any_bfly_fixed<double2, 5>(src, dst, W.data(), n, Ns, jj); break;
-            case 7: any_bfly_fixed<double2, 7>(src, dst, W.data(), n, Ns, jj); break;
-            default: break;
-            }
-         }
-         if (R != 2 && R != 3 && R != 4 && R != 5 && R != 7)
-            for (int o = 0; o < n; o++) dst[o] = any_out_runtime<double2>(src, W.data(), n, R, Ns, o);
-         std::swap(src, dst);
-         Ns *= R;
-      }
-      double err = 0, mx = 0;
-      for (int k = 0; k < n; k++) {
-         long double re = 0, im = 0;
-         for (int j = 0; j < n; j++) {
-            const long double ang = -pi2 * (long double)((long long)j * k % n) / n;
-            re += x[j].x * cosl(ang) - x[j].y * sinl(ang);
-            im += x[j].x * sinl(ang) + x[j].y * cosl(ang);
-         }
-         err = fmax(err, fmax(fabs((double)(src[k].x - re)), fabs((double)(src[k].y - im))));
-         mx = fmax(mx, fmax(fabs((double)re), fabs((double)im)));
-      }
-      printf("n=%5d passes=%d rel err %.2e\n", n, np, err / mx);
-      worst = fmax(worst, err / mx);
-   }
-   printf("worst %.2e\n", worst);
-   return worst < 1e-13 ? 0 : 1;
+   const int sizes[] = {1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 17, 18, 20, 21, 22, 24, 26, 27, 34, 35, 48, 49, 51, 60, 66, 68, 81, 96, 100, 102, 121, 127, 130, 144, 210, 257, 289, 323, 360, 510, 768, 1000, 1001, 1536, 3000};
+   double worst = 0, worst32 = 0;
+   for (int n : sizes) worst = fmax(worst, run<double>(n));
+   for (int n : sizes) worst32 = fmax(worst32, run<float>(n));
+   printf("worst fp64 %.2e, fp32 %.2e\n", worst, worst32);
+   return (worst < 1e-13 && worst32 < 2e-5) ? 0 : 1;
 }
