@@ -298,15 +298,17 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             for (int l = 0; l < LY; l++)
                if (grp * LY + l < ntiles) total += (unsigned)(which ? g2.bytes_late : g2.bytes_early);
             mbar_expect_tx(mb, total);
-            for (int l = 0; l < LY; l++) {
-               const int tile = grp * LY + l;
-               if (tile >= ntiles) break;
-               const int b = tile / tiles_a;
-               const int a0 = (tile - b * tiles_a) * TX;
-               unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
-               for (int i = 0; i < g2.nops; i++) {
-                  const LoadOp &op = g2.ops[i];
-                  if ((op.late & 1) != which) continue;
+            // boxes of the same rows for the LY sub-tiles are requested back to back: adjacent sub-tiles are the two
+            // halves of the same 128-byte lines of a strided pencil
+            for (int i = 0; i < g2.nops; i++) {
+               const LoadOp &op = g2.ops[i];
+               if ((op.late & 1) != which) continue;
+               for (int l = 0; l < LY; l++) {
+                  const int tile = grp * LY + l;
+                  if (tile >= ntiles) break;
+                  const int b = tile / tiles_a;
+                  const int a0 = (tile - b * tiles_a) * TX;
+                  unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
                   unsigned char *dst = zone + (size_t)op.dst_row * G::row_bytes;
                   if (op.late & 2) tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, b, op.c1, mb); // tensor dims ordered (a, b, e)
                   else tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, op.c1, b, mb);

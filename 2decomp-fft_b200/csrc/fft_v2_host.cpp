@@ -196,8 +196,9 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
             const int late = grow >= k->rows_early;
             int room = late ? (rows_total - grow) : (k->rows_early - grow);
             room = std::min(room, len - done);
+            static const int box_rows = std::max(8, std::min(256, env_int("D2D_TMA_BOX_ROWS", 256))); // rows per box (power of two)
             int br = 256;
-            while (br > room) br >>= 1;
+            while (br > room || br > box_rows) br >>= 1;
             const int mi = B.find_or_make(m, br, d, f64, box0);
             if (mi < 0 || a2.nops == kMaxLoadOps) return false;
             LoadOp &op = a2.ops[a2.nops++];
