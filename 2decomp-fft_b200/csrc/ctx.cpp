@@ -28,11 +28,11 @@ const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, i
       if (!k.v2 && k.n == n && k.f64 == f64 && k.kind == kind && k.mode == mode && k.pairvec == pairvec && k.line_in == line_in) return &k;
    return nullptr;
 }
-const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl, int row_bytes)
+const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl, int row_bytes, int merged)
 {
    // row_bytes: bytes of TX adjacent complex lines (64: two blocks per SM; 128: one L2 line per row)
    for (const auto &k : registry())
-      if (k.v2 && k.n == n && k.f64 == f64 && k.mode == mode && k.inl == inl && k.tx * (f64 ? 16 : 8) == row_bytes) return &k;
+      if (k.v2 && k.n == n && k.f64 == f64 && k.mode == mode && k.inl == inl && k.tx * (f64 ? 16 : 8) == row_bytes && k.merged == merged) return &k;
    return nullptr;
 }
 int fft_registry_size() { return (int)registry().size(); }

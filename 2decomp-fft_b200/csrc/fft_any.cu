@@ -20,7 +20,7 @@ std::mutex g_root_mutex;
 std::map<RootKey, void *> g_roots;
 
 constexpr size_t kAnySmemBudget = 200 * 1024; // what the geometry may use
-constexpr size_t kAnySmemMax = 227 * 1024;    // opt-in limit of sm_100a
+constexpr size_t kAnySmemMax = 224 * 1024;    // opt-in limit of sm_100a (227 KB) minus the kernel's static shared memory (line tables)
 
 // W[k] = exp(-2 pi i k / n): octant-reduced so that every entry is accurate to the last bit or so
 const void *roots_for(int device, int n, int f64)

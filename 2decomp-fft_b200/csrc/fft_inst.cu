@@ -90,14 +90,16 @@ constexpr int TX2N = 64 / (int)sizeof(T2);                                 // 64
 constexpr int TX2W = 128 / (int)sizeof(T2);                                // 128-byte tile rows (one L2 line per row)
 constexpr size_t kSmemSM = 227 * 1024;
 
-template <int MODE, int INL, int TX2> struct Inst2 {
+template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
    static constexpr int LY2 = cmax(1, kTargetThreads / (TX2 * P::T));
-   using G = Geom2<real_t, P, TX2, LY2, PADK, MODE, INL>;
-   static constexpr bool fits = PlanInfo<P>::npass >= 2 && P::N >= 256 && G::late_fits && G::threads <= 1024 && G::smem_bytes + 1024 <= kSmemSM;
+   static constexpr bool mrg_ok = !MRG || (INL == IN_TILE && LY2 == 2);
+   using G = Geom2<real_t, P, TX2, LY2, PADK, MODE, INL, MRG && mrg_ok>;
+   static constexpr bool fits = mrg_ok && PlanInfo<P>::npass >= 2 && P::N >= 256 && G::late_fits && G::threads <= 1024 && G::smem_bytes + 1024 <= kSmemSM &&
+                                (!MRG || G::late_all <= G::x_bytes);
    static constexpr int MINB = (G::threads <= 256 && 2 * (G::smem_bytes + 1024) <= kSmemSM) ? 2 : 1;
    static cudaError_t launch(const FftArgs2 &g, const TmapPack &tm, cudaStream_t st)
    {
-      auto kern = fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB>;
+      auto kern = fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB, MRG && mrg_ok>;
       static bool attr_done = false;
       static int resident = 0;
       const size_t smem = G::smem_bytes;
@@ -113,8 +115,8 @@ template <int MODE, int INL, int TX2> struct Inst2 {
          resident = sms * per_sm;
          attr_done = true;
       }
-      const long long tiles = (long long)((g.a.na + TX2 - 1) / TX2) * g.a.nb;
-      const long long groups = (tiles + LY2 - 1) / LY2;
+      const long long tiles_a = (g.a.na + TX2 - 1) / TX2;
+      const long long groups = MRG ? ((tiles_a + LY2 - 1) / LY2) * g.a.nb : (tiles_a * g.a.nb + LY2 - 1) / LY2;
       if (groups <= 0) return cudaSuccess;
       const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
       kern<<<blocks, G::threads, smem, st>>>(g, tm);
@@ -130,7 +132,8 @@ template <int MODE, int INL, int TX2> struct Inst2 {
          k.smem = G::smem_bytes;
          k.tw_total = PlanInfo2<P>::tw_total; k.npass = PI::npass;
          for (int p = 0; p < 4; p++) k.radix[p] = PI::radix(p);
-         k.func = (const void *)fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB>;
+         k.func = (const void *)fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB, MRG && mrg_ok>;
+         k.merged = MRG ? 1 : 0;
          k.line_in = INL == IN_LINE;
          k.launch = nullptr;
          k.v2 = 1; k.inl = INL;
@@ -145,6 +148,8 @@ struct Registrar {
    Registrar()
    {
       Inst2<MODE_C2C, IN_TILE, TX2N>::reg();
+      Inst2<MODE_R2C, IN_TILE, TX2N, true>::reg(); // two adjacent sub-tiles landing as one 128-byte-row box
+      Inst2<MODE_C2C, IN_TILE, TX2N, true>::reg();
       Inst2<MODE_C2C, IN_LINE, TX2N>::reg();
       Inst2<MODE_R2C, IN_TILE, TX2N>::reg();
       Inst2<MODE_R2C, IN_LINE, TX2N>::reg();

@@ -170,7 +170,7 @@ template <typename T, class P, int PASS, int SP, int PADK, class Late> struct Ru
 };
 
 // ---- geometry ---------------------------------------------------------------------------------------
-template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> struct Geom2 {
+template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL, bool MRG = false> struct Geom2 {
    using T2 = typename Vec2<T>::type;
    static constexpr int N = P::N, NH = N / 2 + 1;
    static constexpr int threads = TX * LY * P::T;
@@ -209,7 +209,18 @@ template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL> stru
    // tile can be requested right after the last pass exchange (as in C2C) instead of after the epilogue.
    static constexpr size_t mir_off = (late_skew + late_sub + 15) / 16 * 16;
    static constexpr size_t mir_bytes = (size_t)(padix<PADK>(N / 2 - 1) + 1) * TX * sizeof(T2);
-   static constexpr bool mirror_fits = kV2Mirror && (MODE == MODE_R2C) && (P::E % 2 == 0) && (mir_off + mir_bytes <= x_sub);
+   // MRG (IN_TILE, LY == 2): the LY sub-tiles of a group are ADJACENT along the tile axis and land together -- one TMA
+   // box row carries LY * row_bytes (128 bytes for fp64), shared landing zones: the early one is L as a whole, the late one
+   // spans the front of the exchange buffers (it must fit in front of the mirror regions, which all move into the last
+   // sub-tile's buffer).  The sub-tiles still compute and store on their own (TX-wide lanes, full-width store segments).
+   static constexpr bool merged = MRG;
+   static_assert(!MRG || (INL == IN_TILE && LY >= 2), "merged landing is for tile inputs with several sub-tiles");
+   static constexpr int land_row_bytes = MRG ? LY * row_bytes : row_bytes;
+   static constexpr size_t late_all = (size_t)LY * late_sub; // bytes of the merged late zone
+   static constexpr size_t mir_off_mrg = (size_t)(LY - 1) * x_sub; // mirrors of all sub-tiles: in the last sub-tile's buffer
+   static constexpr bool mirror_fits = kV2Mirror && (MODE == MODE_R2C) && (P::E % 2 == 0) &&
+                                       (MRG ? (late_all <= mir_off_mrg && (size_t)LY * mir_bytes <= x_sub) : (mir_off + mir_bytes <= x_sub));
+   static_assert(!MRG || late_all <= x_bytes, "merged late zone must fit in the exchange buffers");
    static constexpr size_t tw_bytes = ((size_t)PlanInfo2<P>::tw_total * sizeof(T2) + 15) / 16 * 16;
    static constexpr size_t off_x = l_bytes;
    static constexpr size_t off_tw = off_x + x_bytes;
@@ -245,11 +256,11 @@ template <typename T2> struct PieceCursor {
 };
 
 // ---- the kernel -------------------------------------------------------------------------------------
-template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL, int MINB>
+template <typename T, class P, int TX, int LY, int PADK, int MODE, int INL, int MINB, bool MRG = false>
 __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid_constant__ FftArgs2 g2, const __grid_constant__ TmapPack tm)
 {
    using T2 = typename Vec2<T>::type;
-   using G = Geom2<T, P, TX, LY, PADK, MODE, INL>;
+   using G = Geom2<T, P, TX, LY, PADK, MODE, INL, MRG>;
    static_assert(PlanInfo<P>::npass >= 2, "v2 kernels need at least one exchange");
    static_assert(G::late_fits, "the late half of a tile must fit in the exchange buffer of its sub-tile");
    static_assert(MODE == MODE_C2C || INL == IN_TILE || TX % 2 == 0, "real line pairs must land in the same zone");
@@ -270,10 +281,14 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    const int ly = tid / (TX * TPL);
    const int tiles_a = (g.na + TX - 1) / TX;
    const int ntiles = tiles_a * g.nb; // the host guarantees < 2^31
-   const int ngroups = (ntiles + LY - 1) / LY;
+   // MRG: a group is LY tiles adjacent along a, inside one b (groups_a per b); otherwise LY consecutive tiles
+   const int groups_a = (tiles_a + LY - 1) / LY;
+   const int ngroups = MRG ? groups_a * g.nb : (ntiles + LY - 1) / LY;
    T2 *lsm = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub) + tx;
-   const unsigned char *Lmine = Lbase + (size_t)ly * G::l_sub;
-   const unsigned char *Xmine = Xbase + (size_t)ly * G::x_sub + G::late_skew;
+   // landing zones as this thread reads them: row r of the early zone at Lmine + r * land_row_bytes (MRG: the zones are
+   // shared, the sub-tile owns row_bytes at offset ly * row_bytes of every row)
+   const unsigned char *Lmine = MRG ? Lbase + (size_t)ly * G::row_bytes : Lbase + (size_t)ly * G::l_sub;
+   const unsigned char *Xmine = MRG ? Xbase + (size_t)ly * G::row_bytes : Xbase + (size_t)ly * G::x_sub + G::late_skew;
 
    {
       const T2 *__restrict__ twg = reinterpret_cast<const T2 *>(g.tw);
@@ -292,7 +307,21 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    auto issue = [&](int grp, int which) {
       if (noload) return;
       void *mb = &bar[which];
-      if constexpr (INL == IN_TILE) {
+      if constexpr (INL == IN_TILE && MRG) {
+         if (tid == 0) { // one box row = the rows of all LY sub-tiles; columns beyond the batch extent are zero-filled
+            mbar_expect_tx(mb, (unsigned)(which ? g2.bytes_late : g2.bytes_early));
+            const int b = grp / groups_a;
+            const int a0 = (grp - b * groups_a) * (LY * TX);
+            unsigned char *zone = which ? Xbase : Lbase;
+            for (int i = 0; i < g2.nops; i++) {
+               const LoadOp &op = g2.ops[i];
+               if ((op.late & 1) != which) continue;
+               unsigned char *dst = zone + (size_t)op.dst_row * G::land_row_bytes;
+               if (op.late & 2) tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, b, op.c1, mb);
+               else tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, op.c1, b, mb);
+            }
+         }
+      } else if constexpr (INL == IN_TILE) {
          if (tid == 0) {
             unsigned total = 0;
             for (int l = 0; l < LY; l++)
@@ -374,10 +403,19 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    unsigned phase = 0;
    for (; grp < ngroups; grp += gridDim.x, phase ^= 1) {
       T2 v[E];
-      const int tile = grp * LY + ly;
-      const bool in_range = tile < ntiles;
-      const int b = tile / tiles_a;
-      const int a = (tile - b * tiles_a) * TX + tx;
+      int b, a;
+      bool in_range;
+      if constexpr (MRG) {
+         b = grp / groups_a;
+         const int ta = (grp - b * groups_a) * LY + ly;
+         in_range = ta < tiles_a;
+         a = ta * TX + tx;
+      } else {
+         const int tile = grp * LY + ly;
+         in_range = tile < ntiles;
+         b = tile / tiles_a;
+         a = (tile - b * tiles_a) * TX + tx;
+      }
       const bool valid = in_range && a < g.na;
       const bool v1 = valid && (2 * a + 1 < g.na_real);
       const int nxt = grp + (int)gridDim.x;
@@ -393,7 +431,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             const int row = j + TPL * s;
             T2 x;
             if constexpr (INL == IN_TILE) {
-               const unsigned char *src = (row < G::rows_early) ? Lmine + (size_t)row * G::row_bytes : Xmine + (size_t)(row - G::rows_early) * G::row_bytes;
+               const unsigned char *src = (row < G::rows_early) ? Lmine + (size_t)row * G::land_row_bytes : Xmine + (size_t)(row - G::rows_early) * G::land_row_bytes;
                x = reinterpret_cast<const T2 *>(src)[tx];
             } else if constexpr (MODE == MODE_C2C) {
                const unsigned char *line = (tx < G::lines_early) ? Lmine + (size_t)tx * G::line_pitch : Xmine + (size_t)(tx - G::lines_early) * G::line_pitch;
@@ -434,7 +472,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             const int k = lower ? p : N - p;
             T2 A, B;
             if constexpr (INL == IN_TILE) {
-               const unsigned char *src = (k < G::rows_early) ? Lmine + (size_t)k * G::row_bytes : Xmine + (size_t)(k - G::rows_early) * G::row_bytes;
+               const unsigned char *src = (k < G::rows_early) ? Lmine + (size_t)k * G::land_row_bytes : Xmine + (size_t)(k - G::rows_early) * G::land_row_bytes;
                A = reinterpret_cast<const T2 *>(src)[2 * tx];
                B = reinterpret_cast<const T2 *>(src)[2 * tx + 1];
             } else {
@@ -520,7 +558,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          if constexpr (G::mirror_fits) {
             // slots s >= E/2 hold positions >= n/2; they go to mirror index (position - n/2) in the tail of X
             if (!late_done) late();
-            T2 *mir = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub + G::mir_off) + tx;
+            T2 *mir = reinterpret_cast<T2 *>(MRG ? Xbase + G::mir_off_mrg + (size_t)ly * G::mir_bytes : Xbase + (size_t)ly * G::x_sub + G::mir_off) + tx;
 #pragma unroll
             for (int s = E / 2; s < E; s++) mir[padix<PADK>(j + TPL * (s - E / 2)) * SP] = v[s];
             __syncthreads();

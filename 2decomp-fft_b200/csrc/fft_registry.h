@@ -20,13 +20,14 @@ struct FftKernelInfo {
    // v2 (TMA-staged) kernels: fft_kernel_v2.cuh
    int v2 = 0, inl = 0;          // inl: IN_TILE / IN_LINE
    int rows = 0, rows_early = 0, row_bytes = 0; // IN_TILE landing geometry (Geom2)
+   int merged = 0;               // IN_TILE: the LY sub-tiles land together (one box row = ly * row_bytes)
    cudaError_t (*launch2)(const FftArgs2 &, const TmapPack &, cudaStream_t) = nullptr;
 };
 
 void fft_register(const FftKernelInfo &);
 // exact lookup; nullptr if this (n, dtype, kind, mode, pairvec) was not compiled
 const FftKernelInfo *fft_find(int n, int f64, int kind, int mode, int pairvec, int line_in = 0);
-const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl, int row_bytes = 64);
+const FftKernelInfo *fft_find_v2(int n, int f64, int mode, int inl, int row_bytes = 64, int merged = 0);
 int fft_registry_size();
 const FftKernelInfo *fft_registry_at(int i);
 

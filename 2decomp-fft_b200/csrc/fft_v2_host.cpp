@@ -123,9 +123,20 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
    static const int rb_all = env_int("D2D_V2_ROWBYTES", 64), rb_tout = env_int("D2D_V2_ROWBYTES_TILEOUT", 0);
    static const int rb_r2c = env_int("D2D_V2_ROWBYTES_R2C", 0); // experiments: row bytes of r2c stages whose input is a tile
    // default: 128-byte rows for fp64 tile-out stages (one block of 512 threads per SM); fp32 would need 1024 threads
-   int want = tile_out ? (rb_tout ? rb_tout : (f64 ? 128 : 64)) : rb_all;
+   // fp32 tile-out: 128-byte rows need 16 lines = 512 threads and one block per SM; measured (1024^3, profiles/r01_e_kernels_ab.txt)
+   // that pays only when the rows are far apart (the user's Z-pencil: 2.4 vs 5.1 ms), not inside the work buffers
+   const long long out_pitch = (mode == MODE_C2R) ? g.rse * (long long)es : g.out.se[0] * (long long)ces;
+   const int tout_default = f64 ? 128 : (out_pitch >= (1LL << 20) ? 128 : 64);
+   int want = tile_out ? (rb_tout ? rb_tout : tout_default) : rb_all;
    if (rb_r2c && mode == MODE_R2C && inl == IN_TILE) want = rb_r2c;
-   const FftKernelInfo *k = fft_find_v2(g.n, f64, mode, inl, want);
+   // tile inputs: the variant whose two adjacent sub-tiles land as ONE box of 128-byte rows (r2c by default: its rows
+   // are the user's z-lines, 8 MB apart at 1024^3, where 64-byte rows cap the memory system at ~4.2 TB/s, profiles/
+   // r01_c_membench_pitch.txt; D2D_V2_MERGE: 0 never, 1 r2c, 2 r2c and c2c)
+   static const int merge_mode = env_int("D2D_V2_MERGE", 1);
+   const FftKernelInfo *k = nullptr;
+   if (inl == IN_TILE && want == 64 && ((merge_mode >= 1 && mode == MODE_R2C) || (merge_mode >= 2 && mode == MODE_C2C)))
+      k = fft_find_v2(g.n, f64, mode, inl, 64, 1);
+   if (!k) k = fft_find_v2(g.n, f64, mode, inl, want);
    if (!k) k = fft_find_v2(g.n, f64, mode, inl, 64);
    if (!k) return false;
    if ((long long)((g.na + 3) / 4) * g.nb >= (1LL << 31)) return false; // the kernels count tiles in 32 bits
@@ -164,8 +175,9 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       // ---- tile-like: tensor maps + box list ----------------------------------------------------------
       const int np = (mode == MODE_R2C) ? 1 : g.in.np;
       const int rows_total = (mode == MODE_C2R) ? NH : N;
-      const int box0 = k->row_bytes / es; // scalars per landing row
-      a2.c0_mul = box0 / k->tx;
+      const int land_row_bytes = k->merged ? k->ly * k->row_bytes : k->row_bytes;
+      const int box0 = land_row_bytes / es; // scalars per landing row
+      a2.c0_mul = k->row_bytes / es / k->tx; // scalars per line along dim 0
       int row = 0; // global row (along e) of the tile
       a2.nops = 0;
       for (int m = 0; m < np; m++) {
@@ -206,7 +218,7 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
             op.late = (short)(late | (B.swap[mi] << 1));
             op.c1 = done;
             op.dst_row = late ? grow - k->rows_early : grow;
-            op.bytes = br * k->row_bytes;
+            op.bytes = br * land_row_bytes;
             (late ? a2.bytes_late : a2.bytes_early) += op.bytes;
             done += br;
          }
