@@ -73,7 +73,7 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
    auto kern = fft_any_kernel<T, MODE>;
    static size_t smem_set = 0;
    static int sms = 0;
-   if (smem > 48 * 1024 && smem > smem_set) {
+   if (smem + 4096 > 48 * 1024 && smem > smem_set) { // the kernel also has ~2 KB of static shared memory (line tables)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemMax);
       if (e != cudaSuccess) return e;
       smem_set = kAnySmemMax;
