@@ -115,7 +115,7 @@ template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
          resident = sms * per_sm;
          attr_done = true;
       }
-      const long long tiles_a = (g.a.na + TX2 - 1) / TX2;
+      const long long tiles_a = g.tiles_a;
       const long long groups = MRG ? ((tiles_a + LY2 - 1) / LY2) * g.a.nb : (tiles_a * g.a.nb + LY2 - 1) / LY2;
       if (groups <= 0) return cudaSuccess;
       const unsigned blocks = (unsigned)(groups < resident ? groups : resident);

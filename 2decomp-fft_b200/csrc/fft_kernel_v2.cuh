@@ -62,6 +62,11 @@ struct FftArgs2 {
    int c0_mul;               // dim-0 coordinate of a tile = a0 * c0_mul (scalars per line along dim 0)
    int bytes_early, bytes_late; // per sub-tile
    int line_bytes;           // IN_LINE: bytes landed per input line (pieces rounded up to 16 bytes)
+   // C2C only: tile columns shifted per b so that the rows of the TILE side (input of IN_TILE stages, output of IN_LINE
+   // stages) start on full-row boundaries in global memory even when the row pitch of the pencil is odd (the 513-wide
+   // spectral pencils of PHYSICAL_IN_X): first column of tile ta of row b is ta * W - ((shift0 + b * shift_b) mod W),
+   // W = lines per landing row; columns < 0 do not exist.  tiles_a counts the (possibly one more) tiles per b.
+   int shift_on, shift0, shift_b, tiles_a;
    LoadOp ops[kMaxLoadOps];
 };
 
@@ -279,8 +284,11 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    const int tx = tid % TX;
    const int j = (tid / TX) % TPL;
    const int ly = tid / (TX * TPL);
-   const int tiles_a = (g.na + TX - 1) / TX;
+   const int tiles_a = g2.tiles_a;    // (na + TX - 1) / TX, one more per b when the columns are shifted
    const int ntiles = tiles_a * g.nb; // the host guarantees < 2^31
+   constexpr int SW = (MRG ? LY : 1) * TX; // lines per landing row (power of two)
+   const bool shifted = (MODE == MODE_C2C) && g2.shift_on != 0;
+   auto col_shift = [&](int b) { return shifted ? ((g2.shift0 + b * g2.shift_b) & (SW - 1)) : 0; };
    // MRG: a group is LY tiles adjacent along a, inside one b (groups_a per b); otherwise LY consecutive tiles
    const int groups_a = (tiles_a + LY - 1) / LY;
    const int ngroups = MRG ? groups_a * g.nb : (ntiles + LY - 1) / LY;
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          if (tid == 0) { // one box row = the rows of all LY sub-tiles; columns beyond the batch extent are zero-filled
             mbar_expect_tx(mb, (unsigned)(which ? g2.bytes_late : g2.bytes_early));
             const int b = grp / groups_a;
-            const int a0 = (grp - b * groups_a) * (LY * TX);
+            const int a0 = (grp - b * groups_a) * (LY * TX) - col_shift(b);
             unsigned char *zone = which ? Xbase : Lbase;
             for (int i = 0; i < g2.nops; i++) {
                const LoadOp &op = g2.ops[i];
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   const int tile = grp * LY + l;
                   if (tile >= ntiles) break;
                   const int b = tile / tiles_a;
-                  const int a0 = (tile - b * tiles_a) * TX;
+                  const int a0 = (tile - b * tiles_a) * TX - col_shift(b);
                   unsigned char *zone = which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub);
                   unsigned char *dst = zone + (size_t)op.dst_row * G::row_bytes;
                   if (op.late & 2) tma_load_3d(dst, &tm.m[op.map], a0 * g2.c0_mul, b, op.c1, mb); // tensor dims ordered (a, b, e)
@@ -364,7 +372,13 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   if (tile >= ntiles) break;
                   int cnt;
                   if constexpr (SPLIT) cnt = (limit - 2 * ((tile % tiles_a) * TX) + (which ? 0 : 1)) / 2; // lines 2 (a0 + q) + which < limit
-                  else cnt = limit - (((MODE == MODE_C2C) ? 1 : 2) * ((tile % tiles_a) * TX) + lbase);
+                  else if constexpr (MODE != MODE_C2C) cnt = limit - (2 * ((tile % tiles_a) * TX) + lbase);
+                  else { // lines [lo, lo + nl) of this half that exist: 0 <= line < limit (lo < 0 when the columns are shifted)
+                     const int bb = tile / tiles_a;
+                     const int lo = (tile - bb * tiles_a) * TX - col_shift(bb) + lbase;
+                     const int hi = lo + nl < limit ? lo + nl : limit;
+                     cnt = hi - (lo > 0 ? lo : 0);
+                  }
                   lines += (unsigned)(cnt < 0 ? 0 : cnt > nl ? nl : cnt);
                }
                mbar_expect_tx(mb, lines * (unsigned)g2.line_bytes);
@@ -379,8 +393,8 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                if (tile >= ntiles) continue;
                const int b = tile / tiles_a;
                constexpr int lmul = (MODE == MODE_C2C) ? 1 : 2; // input lines per complex line of the tile
-               const int aline = SPLIT ? 2 * ((tile - b * tiles_a) * TX + q) + which : lmul * ((tile - b * tiles_a) * TX) + lbase + q;
-               if (aline >= limit) continue;
+               const int aline = SPLIT ? 2 * ((tile - b * tiles_a) * TX + q) + which : lmul * ((tile - b * tiles_a) * TX) - col_shift(b) + lbase + q;
+               if (aline >= limit || aline < 0) continue;
                unsigned char *dst = (which ? (Xbase + (size_t)l * G::x_sub + G::late_skew) : (Lbase + (size_t)l * G::l_sub)) + (size_t)q * G::line_pitch;
                if constexpr (MODE == MODE_R2C) {
                   const T *src = reinterpret_cast<const T *>(g.rptr) + (long long)aline * g.rsa + (long long)b * g.rsb;
@@ -409,14 +423,14 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
          b = grp / groups_a;
          const int ta = (grp - b * groups_a) * LY + ly;
          in_range = ta < tiles_a;
-         a = ta * TX + tx;
+         a = ta * TX + tx - col_shift(b);
       } else {
          const int tile = grp * LY + ly;
          in_range = tile < ntiles;
          b = tile / tiles_a;
-         a = (tile - b * tiles_a) * TX + tx;
+         a = (tile - b * tiles_a) * TX + tx - col_shift(b);
       }
-      const bool valid = in_range && a < g.na;
+      const bool valid = in_range && a >= 0 && a < g.na;
       const bool v1 = valid && (2 * a + 1 < g.na_real);
       const int nxt = grp + (int)gridDim.x;
 

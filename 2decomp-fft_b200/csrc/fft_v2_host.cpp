@@ -226,6 +226,27 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       }
       if (row != rows_total) return false;
    }
+   // ---- column shift (C2C): make the rows of the tile side start on full-row boundaries -------------------------
+   a2.tiles_a = (g.na + k->tx - 1) / k->tx;
+   static const int shift_enabled = env_int("D2D_V2_SHIFT", 1);
+   if (shift_enabled && mode == MODE_C2C) {
+      const int W = (k->merged ? k->ly : 1) * k->tx; // lines per row of the tile side
+      const void *ptr = nullptr;
+      long long se = 0, sb = 0;
+      if (inl == IN_TILE && g.in.np == 1) { ptr = g.in.ptr[0]; se = g.in.se[0]; sb = g.in.sb[0]; }
+      else if (inl == IN_LINE && tile_out && g.out.np == 1) { ptr = g.out.ptr[0]; se = g.out.se[0]; sb = g.out.sb[0]; }
+      if (ptr && ((uintptr_t)ptr % ces) == 0 && (se % W) == 0 && se > 0 && sb >= 0) {
+         const int off0 = (int)(((uintptr_t)ptr / ces) % W), offb = (int)(sb % W);
+         if (off0 != 0 || (offb != 0 && g.nb > 1)) {
+            a2.shift_on = 1;
+            a2.shift0 = off0;
+            a2.shift_b = offb;
+            a2.tiles_a = (g.na + 2 * k->tx - 2) / k->tx; // room for the partial first tile of a row
+            if (k->merged) a2.tiles_a = ((g.na + W - 1 + W - 1) / W) * k->ly;
+         }
+      }
+   }
+   if ((long long)a2.tiles_a * g.nb >= (1LL << 31)) return false;
    *err = k->launch2(a2, B.tm, ctx->stream);
    return true;
 }
