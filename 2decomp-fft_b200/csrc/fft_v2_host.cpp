@@ -233,7 +233,9 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       const int W = (k->merged ? k->ly : 1) * k->tx; // lines per row of the tile side
       const void *ptr = nullptr;
       long long se = 0, sb = 0;
-      if (inl == IN_TILE && g.in.np == 1) { ptr = g.in.ptr[0]; se = g.in.se[0]; sb = g.in.sb[0]; }
+      // tile INPUTS: measured no gain (TMA boxes are insensitive to the row phase: c2c_z_bwd 3.97 vs 4.10 ms), so only
+      // D2D_V2_SHIFT=2 shifts them; tile OUTPUTS (LSU stores) gain 5.35 -> 3.34 ms (profiles/r01_h_kernels_ab.txt)
+      if (inl == IN_TILE && g.in.np == 1 && shift_enabled >= 2) { ptr = g.in.ptr[0]; se = g.in.se[0]; sb = g.in.sb[0]; }
       else if (inl == IN_LINE && tile_out && g.out.np == 1) { ptr = g.out.ptr[0]; se = g.out.se[0]; sb = g.out.sb[0]; }
       if (ptr && ((uintptr_t)ptr % ces) == 0 && (se % W) == 0 && se > 0 && sb >= 0) {
          const int off0 = (int)(((uintptr_t)ptr / ces) % W), offb = (int)(sb % W);
