@@ -134,7 +134,10 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
    // r01_c_membench_pitch.txt; D2D_V2_MERGE: 0 never, 1 r2c, 2 r2c and c2c)
    static const int merge_mode = env_int("D2D_V2_MERGE", 1);
    const FftKernelInfo *k = nullptr;
-   if (inl == IN_TILE && want == 64 && ((merge_mode >= 1 && mode == MODE_R2C) || (merge_mode >= 2 && mode == MODE_C2C)))
+   // c2c tile inputs take it only when their rows are >= 1 MB apart (the user's Z-pencil read by c2c_z of PHYSICAL_IN_X):
+   // with rows a few KB apart the two-way bank conflict of the shared landing rows costs more than it gives (2.9 -> 3.1 ms)
+   const bool far_rows = mode == MODE_C2C && g.in.np == 1 && g.in.se[0] * (long long)ces >= (1LL << 20);
+   if (inl == IN_TILE && want == 64 && ((merge_mode >= 1 && (mode == MODE_R2C || far_rows)) || (merge_mode >= 2 && mode == MODE_C2C)))
       k = fft_find_v2(g.n, f64, mode, inl, 64, 1);
    if (!k) k = fft_find_v2(g.n, f64, mode, inl, want);
    if (!k) k = fft_find_v2(g.n, f64, mode, inl, 64);
