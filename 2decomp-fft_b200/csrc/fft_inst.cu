@@ -91,8 +91,9 @@ constexpr int TX2W = 128 / (int)sizeof(T2);                                // 12
 constexpr size_t kSmemSM = 227 * 1024;
 
 template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
-   static constexpr int LY2 = cmax(1, kTargetThreads / (TX2 * P::T));
-   static constexpr bool mrg_ok = !MRG || (INL == IN_TILE && LY2 == 2);
+   // merged landing: always two sub-tiles (fp32: 2 x 8 lines = 512 threads; N = 512: two blocks of 128 threads per SM)
+   static constexpr int LY2 = MRG ? 2 : cmax(1, kTargetThreads / (TX2 * P::T));
+   static constexpr bool mrg_ok = !MRG || (INL == IN_TILE);
    using G = Geom2<real_t, P, TX2, LY2, PADK, MODE, INL, MRG && mrg_ok>;
    static constexpr bool fits = mrg_ok && PlanInfo<P>::npass >= 2 && P::N >= 256 && G::late_fits && G::threads <= 1024 && G::smem_bytes + 1024 <= kSmemSM &&
                                 (!MRG || G::late_all <= G::x_bytes);
