@@ -8,6 +8,7 @@
 
 #include "common.h"
 #include "fft_any.cuh"
+#include "fft_registry.h"
 
 namespace d2d {
 
@@ -71,17 +72,20 @@ const void *roots_for(int device, int n, int f64)
 template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, size_t smem, cudaStream_t st)
 {
    auto kern = fft_any_kernel<T, MODE>;
-   static size_t smem_set = 0;
-   static int sms = 0;
-   if (smem + 4096 > 48 * 1024 && smem > smem_set) { // the kernel also has ~2 KB of static shared memory (line tables)
+   // per-device caches (function attributes belong to a device)
+   static bool smem_set_of[kMaxDevices] = {false};
+   static int sms_of[kMaxDevices] = {0};
+   int dev = 0;
+   if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
+   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+   if (smem + 4096 > 48 * 1024 && !smem_set_of[dev]) { // the kernel also has ~2 KB of static shared memory (line tables)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemMax);
       if (e != cudaSuccess) return e;
-      smem_set = kAnySmemMax;
+      smem_set_of[dev] = true;
    }
+   int &sms = sms_of[dev];
    if (!sms) {
-      int dev = 0;
-      cudaError_t e = cudaGetDevice(&dev);
-      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (e != cudaSuccess) return e;
    }
    int per_sm = 0;

@@ -44,23 +44,24 @@ template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
    static cudaError_t launch(const FftArgs &g, cudaStream_t st)
    {
       auto kern = fft_kernel<real_t, P, TX, LY, PADK, MODE, PAIRVEC, MINB, LM>;
-      // per-process caches; every device of this process is the same part running the same binary
-      static bool attr_done = false;
-      static int resident = 0; // blocks that fit on the whole GPU at once (persistent grid)
+      // per-device caches (function attributes belong to a device: a process may drive several, d2d_ctx_create_in_group)
+      static int resident_of[kMaxDevices] = {0}; // blocks that fit on the whole GPU at once (persistent grid); 0 = not set up
       const size_t smem = G::needs_smem ? G::smem_bytes : 0;
-      if (!attr_done) {
+      int dev = 0;
+      if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
+      if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+      int &resident = resident_of[dev];
+      if (!resident) {
          if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
          }
-         int dev = 0, sms = 0, per_sm = 0;
-         cudaError_t e = cudaGetDevice(&dev);
-         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+         int sms = 0, per_sm = 0;
+         cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
          if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
          if (e != cudaSuccess) return e;
          if (per_sm < 1) return cudaErrorLaunchOutOfResources;
          resident = sms * per_sm;
-         attr_done = true;
       }
       const long long tiles = (long long)((g.na + TX - 1) / TX) * g.nb;
       const long long groups = (tiles + LY - 1) / LY;
@@ -101,20 +102,21 @@ template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
    static cudaError_t launch(const FftArgs2 &g, const TmapPack &tm, cudaStream_t st)
    {
       auto kern = fft_kernel_v2<real_t, P, TX2, LY2, PADK, MODE, INL, MINB, MRG && mrg_ok>;
-      static bool attr_done = false;
-      static int resident = 0;
+      static int resident_of[kMaxDevices] = {0}; // per device, 0 = not set up (see Inst::launch)
       const size_t smem = G::smem_bytes;
-      if (!attr_done) {
+      int dev = 0;
+      if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
+      if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+      int &resident = resident_of[dev];
+      if (!resident) {
          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
          if (e != cudaSuccess) return e;
-         int dev = 0, sms = 0, per_sm = 0;
-         e = cudaGetDevice(&dev);
-         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+         int sms = 0, per_sm = 0;
+         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
          if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
          if (e != cudaSuccess) return e;
          if (per_sm < 1) return cudaErrorLaunchOutOfResources;
          resident = sms * per_sm;
-         attr_done = true;
       }
       const long long tiles_a = g.tiles_a;
       const long long groups = MRG ? ((tiles_a + LY2 - 1) / LY2) * g.a.nb : (tiles_a * g.a.nb + LY2 - 1) / LY2;

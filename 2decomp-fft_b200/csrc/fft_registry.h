@@ -7,6 +7,8 @@
 
 namespace d2d {
 
+constexpr int kMaxDevices = 64; // per-device launch caches
+
 enum FftKind { KIND_LINE = 0 /* TX = 1, contiguous lines */, KIND_TILE = 1 /* TX > 1, strided lines */, KIND_TILE_WIDE = 2 /* 2x wider tile rows */ };
 
 struct FftKernelInfo {
