@@ -68,6 +68,26 @@ template <> struct Vec2<double> { using type = double2; };
 
 template <typename T2> D2D_HD T2 cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
 template <typename T2> D2D_HD T2 csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
+// fp32: one packed FADD2 per complex add / subtract on sm_100a (the fp32 kernels are bound by instruction issue, not by HBM:
+// same instruction count as fp64 for half the bytes).  -DD2D_NO_F32X2 builds the scalar version for A/B runs.
+#if defined(__CUDA_ARCH__) && !defined(D2D_NO_F32X2)
+template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b)
+{
+   float2 r;
+   asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+       : "=f"(r.x), "=f"(r.y)
+       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+   return r;
+}
+template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b)
+{
+   float2 r;
+   asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+       : "=f"(r.x), "=f"(r.y)
+       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+   return r;
+}
+#endif
 template <typename T2> D2D_HD T2 cmul(T2 a, T2 b) { return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 // multiply by -i : (x,y) -> (y,-x)
 template <typename T2> D2D_HD T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }
