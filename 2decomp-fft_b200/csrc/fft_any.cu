@@ -2,6 +2,7 @@
 // the table of n-th roots of unity, launch.  Used by run_stage (fft_plan.cpp) for every transform length
 // without a compiled power-of-two kernel.
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -160,7 +161,8 @@ cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
    // within the shared-memory budget; narrower (never below the row width) when that lets two blocks share an SM
    auto smem_of = [&](int lines) { return ces * ((size_t)n + 2 * (size_t)lines * ga.pitch); };
    auto pow2_ceil = [](long long v) { int l = 0; while ((1LL << l) < v) l++; return l; };
-   const int want_rows_log2 = pow2_ceil((long long)(128 / ces));
+   static const int row_bytes = getenv("D2D_ANY_ROW_BYTES") ? atoi(getenv("D2D_ANY_ROW_BYTES")) : 128; // experiments: 64 halves the tile
+   const int want_rows_log2 = pow2_ceil((long long)(std::max(16, row_bytes) / (int)ces));
    int ll = std::max(want_rows_log2, pow2_ceil((2048 + n - 1) / n));
    ll = std::min(ll, pow2_ceil(kAnyMaxLines));
    ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
