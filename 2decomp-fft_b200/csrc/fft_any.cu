@@ -167,7 +167,10 @@ cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
    ll = std::min(ll, pow2_ceil(kAnyMaxLines));
    ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
    while (ll > 0 && smem_of(1 << ll) > kAnySmemBudget) ll--;
-   while (ll > want_rows_log2 && smem_of(1 << ll) > 100 * 1024) ll--;
+   // two blocks per SM (one loads / stores while the other computes) are worth more than 128-byte rows: 510^3 pair 14.4 ->
+   // 11.4 ms with 64-byte rows (profiles/r01_l_any_and_transposes.txt)
+   const int min_rows_log2 = pow2_ceil((long long)(64 / ces));
+   while (ll > min_rows_log2 && smem_of(1 << ll) > 110 * 1024) ll--;
    ga.lines_log2 = ll;
    const size_t smem = smem_of(1 << ll);
    if (mode == MODE_C2C) return f64 ? launch_any<double, MODE_C2C>(ga, smem, ctx->stream) : launch_any<float, MODE_C2C>(ga, smem, ctx->stream);
