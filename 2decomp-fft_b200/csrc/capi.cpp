@@ -440,6 +440,17 @@ int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int cons
    fft_stage_batch(decomp->d, pencil, *na, *nb);
    D2D_CATCH
 }
+int d2d_debug_link_chunk(const d2d_decomp *decomp, int pencil, int other, int padq, int f0, int f1, int *np, int *axis_is_a, int *nf,
+                         int64_t off[8], int64_t cnt[8])
+{
+   D2D_TRY
+   D2D_REQUIRE((pencil == 1 && (other == 0 || other == 2)) || (other == 1 && (pencil == 0 || pencil == 2)), "not a link");
+   LinkChunk c;
+   fft_link_chunk(decomp->d, pencil, other, padq, f0, f1, c);
+   *np = c.np; *axis_is_a = c.axis_is_a; *nf = c.nf;
+   for (int p = 0; p < c.np; p++) { off[p] = c.off[p]; cnt[p] = c.cnt[p]; }
+   D2D_CATCH
+}
 int d2d_debug_user_map(const d2d_decomp *decomp, int pencil, int64_t *se, int64_t *sa, int64_t *sb, int *n, int *na, int *nb)
 {
    D2D_TRY

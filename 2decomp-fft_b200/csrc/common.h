@@ -176,6 +176,11 @@ struct LinkSide {
    long long se[kMaxP], sa[kMaxP], sb[kMaxP];
 };
 void fft_link_side(const Decomp &d, int pencil, int other, int padq, LinkSide &L);
+struct LinkChunk {
+   int np, me, axis_is_a, nf; // axis_is_a: the free axis is batch axis a (else b) of the stage on `pencil`; nf: its extent
+   int64_t off[kMaxP], cnt[kMaxP];
+};
+void fft_link_chunk(const Decomp &d, int pencil, int other, int padq, int f0, int f1, LinkChunk &C);
 int64_t fft_work_elems(const Decomp &d, int padq);
 PieceMap fft_link_map(const Decomp &d, int pencil, int other, void *peers_buf, void *self_buf, int es, bool consumer, int padq);
 void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int padq);

@@ -224,6 +224,35 @@ void fft_link_side(const Decomp &d, int pencil, int other, int padq, LinkSide &L
    L.total = disp;
 }
 
+// Chunk of a link along its FREE axis -- the axis neither stage of the link transforms: x for Z<->Y, z for Y<->X.  It is the
+// slowest axis of every block (see the layouts above), so lines f0 <= f < f1 of the free axis occupy one contiguous
+// sub-range of every block: element offset off[m] = disp[m] + f0 * plane[m], length cnt[m] = (f1 - f0) * plane[m].  The
+// free axis is batch axis `a` of the Z stage (Z<->Y) and of the Y stage (Y<->X), batch axis `b` of the other stage of the
+// link; its extent nf is the same on both sides of the link and on every rank of the communicator.  This is the geometry
+// of the chunk-wise overlap of an exchange with its neighbouring stages: a producer restricted to
+// [f0, f1) writes exactly these sub-ranges, the exchange moves them, a consumer restricted to [f0, f1) reads nothing else.
+void fft_link_chunk(const Decomp &d, int pencil, int other, int padq, int f0, int f1, LinkChunk &C)
+{
+   LinkSide L;
+   fft_link_side(d, pencil, other, padq, L);
+   int na = 0, nb = 0;
+   fft_stage_batch(d, pencil, na, nb);
+   C = LinkChunk{};
+   C.np = L.np;
+   C.me = L.me;
+   // Z<->Y: free axis x = a of the Z stage, b of the Y stage;  Y<->X: free axis z = a of the Y stage, b of the X stage
+   C.axis_is_a = (pencil == 2 || (pencil == 1 && other == 0)) ? 1 : 0;
+   C.nf = C.axis_is_a ? na : nb;
+   D2D_REQUIRE(0 <= f0 && f0 <= f1 && f1 <= C.nf, "chunk outside the free axis");
+   for (int p = 0; p < L.np; p++) {
+      const int64_t plane = C.nf ? L.cnt[p] / C.nf : 0; // elements of block p per line of the free axis
+      D2D_REQUIRE(plane * C.nf == L.cnt[p], "block size is not a multiple of the free-axis extent");
+      D2D_REQUIRE((C.axis_is_a ? L.sa[p] : L.sb[p]) == plane || L.cnt[p] == 0, "free axis is not the slowest axis of the block");
+      C.off[p] = L.disp[p] + (int64_t)f0 * plane;
+      C.cnt[p] = (int64_t)(f1 - f0) * plane;
+   }
+}
+
 // largest buffer (in elements) any stage of a 3-D transform on this decomp writes or receives
 int64_t fft_work_elems(const Decomp &d, int padq)
 {

@@ -151,6 +151,12 @@ int d2d_fft_kernel_describe(int i, char *buf, int buflen);
  * their unit-stride axis, so these are NOT the reference's x1cnts... tables). */
 int d2d_debug_link_map(const d2d_decomp *decomp, int pencil, int other, int consumer, int padq, int *np, int e0[9], int64_t off[8],
                        int in_self[8], int64_t se[8], int64_t sa[8], int64_t sb[8], int *na, int *nb, int64_t cnt[8], int64_t disp[8]);
+/* Chunk [f0, f1) of a link along its free axis (the axis neither stage of the link transforms: x for Z<->Y, z for Y<->X;
+ * batch axis a of the stage when axis_is_a = 1, else b; extent nf): the contiguous element sub-range off[m], cnt[m] of every
+ * block m that a producer restricted to the chunk writes / a consumer restricted to it reads (chunk-wise overlap of the
+ * exchange with its neighbouring stages; host arithmetic only). */
+int d2d_debug_link_chunk(const d2d_decomp *decomp, int pencil, int other, int padq, int f0, int f1, int *np, int *axis_is_a, int *nf,
+                         int64_t off[8], int64_t cnt[8]);
 /* the user's dense pencil seen with the same (a,b) convention */
 int d2d_debug_user_map(const d2d_decomp *decomp, int pencil, int64_t *se, int64_t *sa, int64_t *sb, int *n, int *na, int *nb);
 
