@@ -39,7 +39,8 @@ const std::string &get_last_error();
 
 constexpr int kMaxP = kMaxPieces; // max ranks along one side of the process grid
 constexpr int kMaxRanks = kMaxPieces * kMaxPieces;
-constexpr int kWorkBuffers = 3;
+constexpr int kWorkBuffers = 3;  // rotated by the chains and mapped between ranks (p2p.cpp)
+constexpr int kCtxBuffers = 4;   // + one more for the overlapped chain on two-dimensional process grids (never mapped)
 
 // decomp_info (src/info.f90:19-47).  0-based starts internally; the C ABI converts to 1-based.
 struct Decomp {
@@ -101,9 +102,12 @@ struct Ctx {
    bool blocking = true;
    int64_t launches = 0;
    // grow-only work buffers (the reference's work1/work2 high-water mark, src/decomp_2d.f90:461-485)
-   void *work[kWorkBuffers] = {nullptr, nullptr, nullptr};
-   size_t work_bytes[kWorkBuffers] = {0, 0, 0};
+   void *work[kCtxBuffers] = {nullptr, nullptr, nullptr, nullptr};
+   size_t work_bytes[kCtxBuffers] = {0, 0, 0, 0};
    struct P2P *p2p = nullptr; // peer-mapped work buffers + flags (p2p.cpp); null when unused
+   // chunk-wise overlapped chains (fft_plan.cpp run_chain_overlap): the exchanges run on their own stream
+   cudaStream_t comm_stream = nullptr;
+   std::vector<cudaEvent_t> sync_events; // untimed events ordering the two streams, reused between calls
    // profiling
    bool profiling = false;
    std::vector<ProfEntry> prof;

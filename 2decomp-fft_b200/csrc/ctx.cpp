@@ -159,9 +159,11 @@ Ctx::~Ctx()
    if (p2p) p2p_destroy(p2p);
    p2p = nullptr;
    tr.reset();
+   if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
+   for (auto e : sync_events) cudaEventDestroy(e);
    for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
    for (auto e : event_pool) cudaEventDestroy(e);
-   for (int i = 0; i < 3; i++)
+   for (int i = 0; i < kCtxBuffers; i++)
       if (work[i]) cudaFree(work[i]);
    if (stream) cudaStreamDestroy(stream);
 }

@@ -34,8 +34,14 @@ static const int *pencil_size(const Decomp &d, int p) { return p == 0 ? d.xsz : 
 // neighbouring mem_split_* / mem_merge_* through the maps.  `chain`: the stage is part of a 3-D
 // transform and uses the (a,b) batch convention of the private wire layouts (decomp.cpp); otherwise
 // it works on one dense local array.
+// `rg` restricts a chain stage to lines f0 <= f < f1 of one batch axis (0 = a, 1 = b; -1 = the whole batch): the chunks of the
+// overlapped chain (run_chain_overlap).  Along `a` a real transform needs an even f0 (real lines are transformed in pairs).
+struct StageRange {
+   int axis = -1, f0 = 0, f1 = 0;
+};
+
 static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc, const Decomp *dr, const PieceMap &in,
-                      const PieceMap &out, void *rptr, int backward, int passthrough, bool chain)
+                      const PieceMap &out, void *rptr, int backward, int passthrough, bool chain, StageRange rg = StageRange())
 {
    const int *cs = pencil_size(dc, pencil);
    FftArgs g{};
@@ -52,17 +58,27 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    } else if (pencil == 0) { g.na = cs[1] * cs[2]; g.nb = 1; kind = KIND_LINE; }
    else if (pencil == 1) { g.na = cs[0]; g.nb = cs[2]; kind = KIND_TILE; }
    else { g.na = cs[0] * cs[1]; g.nb = 1; kind = KIND_TILE; }
+   const int rs = f64 ? 8 : 4;
+   if (rg.axis >= 0) {
+      D2D_REQUIRE(chain && rg.f0 >= 0 && rg.f0 <= rg.f1 && rg.f1 <= (rg.axis == 0 ? g.na : g.nb), "invalid stage range");
+      D2D_REQUIRE(mode == MODE_C2C || rg.axis == 1 || rg.f0 % 2 == 0, "a real stage starts its chunks on even lines");
+      auto advance = [&](PieceMap &m) {
+         for (int q = 0; q < m.np; q++)
+            m.ptr[q] = (char *)m.ptr[q] + (long long)(2 * rs) * rg.f0 * (rg.axis == 0 ? m.sa[q] : m.sb[q]);
+      };
+      advance(g.in);
+      advance(g.out);
+      (rg.axis == 0 ? g.na : g.nb) = rg.f1 - rg.f0;
+   }
    const long long lines = (long long)g.na * g.nb;
    int n = cs[pencil];
    int pairvec = 0;
-   const int rs = f64 ? 8 : 4;
    double bytes = 2.0 * (double)lines * n * 2 * rs;
    if (mode != MODE_C2C) {
       D2D_REQUIRE(dr != nullptr && (pencil == 0 || pencil == 2), "real transforms run along x or z only");
       const int *rsz = pencil_size(*dr, pencil);
       n = rsz[pencil];
       D2D_REQUIRE(cs[pencil] == n / 2 + 1, "complex extent must be n/2+1 along the real-transform axis");
-      g.rptr = rptr;
       g.na_real = g.na;
       g.na = (g.na_real + 1) / 2;
       const long long r1 = rsz[0], r12 = (long long)rsz[0] * rsz[1];
@@ -70,6 +86,10 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
          g.rse = 1; g.rsa = r1; g.rsb = chain ? r12 : 0;
       } else { // lines along z; chain: a = x, b = y; dense: a = (x,y) flattened
          g.rse = r12; g.rsa = 1; g.rsb = chain ? r1 : 0;
+      }
+      if (rg.axis >= 0) rptr = (char *)rptr + (long long)rs * rg.f0 * (rg.axis == 0 ? g.rsa : g.rsb);
+      g.rptr = rptr;
+      if (pencil != 0) {
          // pairs (a, a+1) are adjacent reals: one vector access when every pair is 2*sizeof(T) aligned
          const bool even_rows = chain ? (r1 % 2 == 0) : (r12 % 2 == 0);
          pairvec = (even_rows && ((uintptr_t)rptr % (2 * rs)) == 0) ? 1 : 0;
@@ -112,10 +132,155 @@ struct StageDef {
 static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward);
 static size_t uniform_work_bytes(const Plan &p, bool c2c);
 
+// ---- chunk-wise overlap of the exchanges with their neighbouring stages (opt-in: D2D_OVERLAP=<chunks>, NCCL / in-process
+// transports) ---------------------------------------------------------------------------------------------------------
+// Every link with more than one rank is cut into K chunks along its free axis (fft_link_chunk: contiguous sub-ranges of
+// every block).  The producer runs chunk by chunk on the context's stream; as soon as chunk c is written its sub-ranges are
+// exchanged on the communication stream while the producer works on chunk c + 1.  The consumer of a link follows chunk by
+// chunk as the exchanges complete -- unless it is itself the chunked producer of the next link (the middle stage of a
+// p_row > 1, p_col > 1 grid: its input chunks run along x, its output chunks along z), in which case it starts after the
+// last chunk of its input has arrived.  Work-buffer rotation and maps are those of run_chain.
+static int overlap_chunks()
+{
+   const char *v = getenv("D2D_OVERLAP"); // read per call: tests switch it at run time
+   const int k = v ? atoi(v) : 0;
+   return k > 64 ? 64 : k;
+}
+
+static void run_chain_overlap(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward, int K)
+{
+   Ctx *ctx = p.ctx;
+   const int es = p.f64 ? 16 : 8;
+   const int padq = 128 / es;
+   const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
+   if (!ctx->comm_stream) D2D_CHECK_CUDA(cudaStreamCreate(&ctx->comm_stream));
+   size_t next_event = 0;
+   auto new_event = [&]() {
+      if (next_event == ctx->sync_events.size()) {
+         cudaEvent_t e;
+         D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+         ctx->sync_events.push_back(e);
+      }
+      return ctx->sync_events[next_event++];
+   };
+   const bool real_link[2] = {comm_size(dc, st[0].pencil, st[1].pencil) > 1, comm_size(dc, st[1].pencil, st[2].pencil) > 1};
+   // chunk boundaries of a link: K pieces of the free axis, cut on multiples of 16 lines (tiles and real pairs stay whole)
+   // Always K chunks (empty ones allowed): every rank of the grid then issues the same number of exchanges whatever its
+   // own extents are, which the in-process transport (one barrier over all ranks per exchange) relies on.
+   auto bounds = [&](int nf) {
+      std::vector<int> b(K + 1, 0);
+      for (int c = 1; c < K; c++) b[c] = std::max(b[c - 1], (int)((long long)nf * c / K) / 16 * 16);
+      b[K] = nf;
+      return b;
+   };
+   // work buffers holding the current stage's input (self block / received blocks).  A chunked producer still reads them
+   // while its first chunks are being exchanged, so it needs two MORE buffers (send, receive): four on a 2-D process grid.
+   int live_a = -1, live_b = -1;
+   auto pick = [&](int avoid) {
+      for (int i = 0; i < kCtxBuffers; i++)
+         if (i != live_a && i != live_b && i != avoid) return i;
+      return -1;
+   };
+   PieceMap cur = fft_user_map(dc, st[0].pencil, in);
+   std::vector<cudaEvent_t> arrived;       // per chunk of the link feeding the current stage: its exchange has completed
+   std::vector<int> arrived_bounds;        // chunk boundaries of that link
+   for (int s = 0; s < 3; s++) {
+      const int pen = st[s].pencil, mode = st[s].mode;
+      const bool last = (s == 2);
+      const int passthrough = (mode == MODE_C2C && p.skip[pen]) ? 1 : 0;
+      PieceMap om{};
+      void *rptr = nullptr, *sendbuf = nullptr;
+      int send_w = -1;
+      if (mode == MODE_R2C) rptr = in;
+      if (last) {
+         if (mode == MODE_C2R) rptr = out;
+         else om = fft_user_map(dc, pen, out);
+      } else {
+         send_w = pick(-1);
+         sendbuf = ctx->reserve(send_w, wbytes);
+         om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false, padq);
+      }
+      const bool produce_chunked = !last && real_link[s];
+      const bool consume_chunked = !arrived.empty() && !produce_chunked;
+      void *recvbuf = nullptr;
+      int recv_w = -1;
+      if (produce_chunked) {
+         const int nxt = st[s + 1].pencil;
+         recv_w = pick(send_w);
+         D2D_REQUIRE(recv_w >= 0 && recv_w != send_w, "overlapped chain: no free work buffer");
+         recvbuf = ctx->reserve(recv_w, wbytes);
+         if (!arrived.empty()) { // the whole input must be here before the first chunk
+            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived.back(), 0));
+            arrived.clear();
+         }
+         LinkChunk probe;
+         fft_link_chunk(dc, pen, nxt, padq, 0, 0, probe);
+         const std::vector<int> b = bounds(probe.nf);
+         std::vector<cudaEvent_t> done;
+         const bool col = (pen == 0 || nxt == 0);
+         for (size_t c = 0; c + 1 < b.size(); c++) {
+            StageRange rg;
+            rg.axis = probe.axis_is_a ? 0 : 1; rg.f0 = b[c]; rg.f1 = b[c + 1];
+            run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true, rg);
+            cudaEvent_t written = new_event();
+            D2D_CHECK_CUDA(cudaEventRecord(written, ctx->stream));
+            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, written, 0));
+            LinkChunk S, R;
+            fft_link_chunk(dc, pen, nxt, padq, b[c], b[c + 1], S);
+            fft_link_chunk(dc, nxt, pen, padq, b[c], b[c + 1], R);
+            std::vector<PeerXfer> xf;
+            for (int k = 1; k < S.np; k++) {
+               const int m = (S.me + k) % S.np;
+               PeerXfer x;
+               x.peer = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
+               x.sendptr = (const char *)sendbuf + (size_t)es * S.off[m];
+               x.sendbytes = (size_t)es * S.cnt[m];
+               x.recvptr = (char *)recvbuf + (size_t)es * R.off[m];
+               x.recvbytes = (size_t)es * R.cnt[m];
+               xf.push_back(x);
+            }
+            ctx->tr->exchange(xf, ctx->comm_stream);
+            cudaEvent_t e = new_event();
+            D2D_CHECK_CUDA(cudaEventRecord(e, ctx->comm_stream));
+            done.push_back(e);
+         }
+         arrived = done;
+         arrived_bounds = b;
+         live_a = send_w;
+         live_b = recv_w;
+         cur = fft_link_map(dc, nxt, pen, recvbuf, sendbuf, es, true, padq);
+         continue;
+      }
+      if (consume_chunked) { // chunk by chunk as the exchanges of the feeding link complete (same free axis, seen from this side)
+         LinkChunk probe;
+         fft_link_chunk(dc, pen, st[s - 1].pencil, padq, 0, 0, probe);
+         for (size_t c = 0; c + 1 < arrived_bounds.size(); c++) {
+            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived[c], 0));
+            StageRange rg;
+            rg.axis = probe.axis_is_a ? 0 : 1; rg.f0 = arrived_bounds[c]; rg.f1 = arrived_bounds[c + 1];
+            run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true, rg);
+         }
+         arrived.clear();
+      } else {
+         if (!arrived.empty()) {
+            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived.back(), 0));
+            arrived.clear();
+         }
+         run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+      }
+      if (last) break;
+      // a link inside one rank: the consumer reads what this stage wrote
+      live_a = send_w;
+      live_b = -1;
+      cur = fft_link_map(dc, st[s + 1].pencil, pen, nullptr, sendbuf, es, true, padq);
+   }
+}
+
 static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
    Ctx *ctx = p.ctx;
    if (p2p_active(ctx)) return run_chain_p2p(p, dc, dr, st, in, out, backward);
+   if (overlap_chunks() > 1 && ctx->nranks > 1) return run_chain_overlap(p, dc, dr, st, in, out, backward, overlap_chunks());
    const int es = p.f64 ? 16 : 8;
    const int padq = 128 / es;
    const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
