@@ -16,7 +16,8 @@ bk f64 --n 1024 --reps 5 --only3d
 bk f32 --n 1024 --prec f32 --reps 5 --only3d
 if [ "$1" != "quick" ]; then
 timeout 200 python -u bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; cat $O/bench_ref.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $O/bench_under_ncu.log 2>&1
+# only the library's kernels (torch's RNG / reduction kernels of the bench harness would eat the launch budget): 3 pairs = 18 launches
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fft_ -c 40 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $O/bench_under_ncu.log 2>&1
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:fft_kernel -s 6 -c 6 -o $O/prof_pair -f python tools/run_pair.py 1024 1024 1024 z f64 2 > $O/ncu_full.log 2>&1
 tail -2 $O/ncu_full.log
 fi
