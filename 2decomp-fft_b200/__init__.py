@@ -85,6 +85,7 @@ def lib():
         l.d2d_fft_r2c_1m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.d2d_fft_c2r_1m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.d2d_ctx_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.d2d_ctx_create_bootstrap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.d2d_ctx_create_in_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         l.d2d_ctx_destroy.argtypes = [C.c_void_p]
         l.d2d_ctx_sync.argtypes = [C.c_void_p]
@@ -204,6 +205,31 @@ def _dtype_code(t):
     raise Decomp2dError(2, f"unsupported dtype {t.dtype}")
 
 
+_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+def _allgather_callback(fn):
+    """C callback (d2d_allgather_fn) around fn(bytes) -> [bytes of rank 0, bytes of rank 1, ...]."""
+    def cb(_user, send, recv, nbytes):
+        try:
+            parts = fn(C.string_at(send, nbytes))
+            blob = b"".join(parts)
+            C.memmove(recv, blob, len(blob))
+            return 0
+        except Exception:  # the C side turns this into a Decomp2dError
+            import traceback
+            traceback.print_exc()
+            return 1
+    return _ALLGATHER_FN(cb)
+
+
+def _check_dtype(t, engine_dtype, what):
+    torch = _torch()
+    want = {torch.float64: (torch.float64, torch.complex128), torch.float32: (torch.float32, torch.complex64)}[engine_dtype]
+    if t.dtype not in want:
+        raise Decomp2dError(2, f"{what}: dtype {t.dtype} does not match the engine precision {engine_dtype}")
+
+
 def _check_pencil(t, shape, what):
     if tuple(t.shape) != tuple(shape):
         raise Decomp2dError(2, f"{what}: array shape {tuple(t.shape)} does not match the pencil {tuple(shape)}")
@@ -217,7 +243,9 @@ def _check_pencil(t, shape, what):
 class Decomp2d:
     """One rank's library state: what decomp_2d_init sets up (src/decomp_2d_init_fin.f90:15-184)."""
 
-    def __init__(self, nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None):
+    def __init__(self, nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None):
+        """unique_id: NCCL bootstrap (d2d_ctx_create); group: thread-per-rank ranks of one process; allgather: a callable
+        bytes -> [bytes per rank] (MPI_Allgather-like) for the NCCL-free bootstrap (d2d_ctx_create_bootstrap)."""
         torch = _torch()
         l = lib()
         if p_row <= 0 or p_col <= 0:  # auto-tuning mode (decomp_2d_init_fin.f90:55-77)
@@ -226,8 +254,13 @@ class Decomp2d:
             device = torch.cuda.current_device()
         self.device = device
         self._h = C.c_void_p()
+        self._allgather_cb = None
         if group is not None:
             _check(l.d2d_ctx_create_in_group(C.byref(self._h), group._h, rank, p_row, p_col, device))
+        elif allgather is not None:
+            self._allgather_cb = _allgather_callback(allgather)  # must outlive the context
+            _check(l.d2d_ctx_create_bootstrap(C.byref(self._h), nranks, rank, p_row, p_col, device,
+                                              C.cast(self._allgather_cb, C.c_void_p), None))
         else:
             idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
             _check(l.d2d_ctx_create(C.byref(self._h), idbuf, nranks, rank, p_row, p_col, device))
@@ -286,19 +319,39 @@ class Decomp2d:
         self._transpose(Y_TO_X, src, dst, decomp)
 
     # bare batched 1-D transforms on a local array (c2c_1m_x/y/z ..., src/fft_cufft.f90:489-671)
+    @staticmethod
+    def _check_1m(a, out, shape_a, shape_out):
+        for t, shp, what in ((a, shape_a, "in"), (out, shape_out, "out")):
+            _check_pencil(t, shp, what)
+        if _dtype_code(a) != _dtype_code(out):
+            raise Decomp2dError(2, "in and out must have the same precision")
+
     def c2c_1m(self, a, axis, isign, out=None):
         out = a if out is None else out
         n1, n2, n3 = a.shape
+        self._check_1m(a, out, a.shape, a.shape)
+        if not (a.is_complex() and out.is_complex()):
+            raise Decomp2dError(2, "c2c_1m works on complex arrays")
         _check(lib().d2d_fft_c2c_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr(), isign))
         return out
 
     def r2c_1m(self, a, out, axis):
         n1, n2, n3 = a.shape
+        cs = [n1, n2, n3]
+        cs[axis] = cs[axis] // 2 + 1
+        self._check_1m(a, out, a.shape, cs)
+        if a.is_complex() or not out.is_complex():
+            raise Decomp2dError(2, "r2c_1m: real input, complex output")
         _check(lib().d2d_fft_r2c_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr()))
         return out
 
     def c2r_1m(self, a, out, axis):
         n1, n2, n3 = out.shape
+        cs = [n1, n2, n3]
+        cs[axis] = cs[axis] // 2 + 1
+        self._check_1m(a, out, cs, out.shape)
+        if not a.is_complex() or out.is_complex():
+            raise Decomp2dError(2, "c2r_1m: complex input, real output")
         _check(lib().d2d_fft_c2r_1m(self._h, _dtype_code(a), axis, n1, n2, n3, a.data_ptr(), out.data_ptr()))
         return out
 
@@ -395,6 +448,10 @@ class Decomp2dFFTEngine:
     # decomp_2d_fft_3d generic interface (src/fft_common.f90:31-38): (in_c,out_c,isign) | (in_r,out_c) | (in_c,out_r)
     def fft_3d(self, inp, out, isign=None):
         fx = self.format == PHYSICAL_IN_X
+        _check_dtype(inp, self.dtype, "in")
+        _check_dtype(out, self.dtype, "out")
+        if inp.data_ptr() == out.data_ptr() and inp.numel():
+            raise Decomp2dError(2, "decomp_2d_fft_3d: in and out must be different arrays (the input is preserved)")
         if inp.is_complex() and out.is_complex():
             if isign not in (DECOMP_2D_FFT_FORWARD, DECOMP_2D_FFT_BACKWARD):
                 raise Decomp2dError(1, "c2c transforms need isign = DECOMP_2D_FFT_FORWARD / _BACKWARD")
@@ -433,19 +490,32 @@ class Decomp2dFFTEngine:
 _state = threading.local()
 
 
-def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None):
-    _state.d2d = Decomp2d(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, unique_id=unique_id, device=device, group=group)
+def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None):
+    _state.d2d = Decomp2d(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, unique_id=unique_id, device=device, group=group,
+                          allgather=allgather)
     _state.engines = {}
     _state.current = None
     return _state.d2d
 
 
-def decomp_2d_init_from_torch_distributed(nx, ny, nz, p_row, p_col):
-    """decomp_2d_init for a torchrun job: the unique id travels through torch.distributed
-    (any backend), standing in for the MPI_Bcast of src/decomp_2d_nccl.f90:185."""
+def decomp_2d_init_from_torch_distributed(nx, ny, nz, p_row, p_col, transport=None):
+    """decomp_2d_init for a torchrun job.  transport "nccl" (default on an NCCL process group): the unique id travels
+    through torch.distributed, standing in for the MPI_Bcast of src/decomp_2d_nccl.f90:185, and NCCL stays available as the
+    second data plane (D2D_P2P=0).  transport "boot" (default on any other process group, or D2D_TRANSPORT=boot): no NCCL at
+    all -- torch.distributed only all-gathers the CUDA-IPC handles at plan creation (what MPI_Allgather does in the Fortran
+    shim) and the exchange is the library's own peer-memory path."""
     torch = _torch()
     import torch.distributed as dist
     rank, nranks = dist.get_rank(), dist.get_world_size()
+    if transport is None:
+        transport = os.environ.get("D2D_TRANSPORT") or ("nccl" if dist.get_backend() == "nccl" else "boot")
+    if transport == "boot" and nranks > 1:
+        def allgather(data):
+            parts = [None] * nranks
+            dist.all_gather_object(parts, data)
+            return parts
+        return decomp_2d_init(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, device=torch.cuda.current_device(),
+                              allgather=allgather)
     obj = [get_unique_id() if rank == 0 else None]
     if nranks > 1:
         dist.broadcast_object_list(obj, src=0)

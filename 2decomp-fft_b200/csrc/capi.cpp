@@ -81,6 +81,19 @@ int d2d_ctx_create(d2d_ctx **ctx, const unsigned char id[128], int nranks, int r
    D2D_CATCH
 }
 
+int d2d_ctx_create_bootstrap(d2d_ctx **ctx, int nranks, int rank, int p_row, int p_col, int device, d2d_allgather_fn allgather, void *user)
+{
+   D2D_TRY
+   std::unique_ptr<d2d_ctx> h(new d2d_ctx());
+   ctx_common_init(h.get(), nranks, rank, p_row, p_col, device);
+   if (nranks > 1) {
+      D2D_REQUIRE(allgather != nullptr, "an all-gather callback is required for nranks > 1");
+      h->c.tr.reset(make_boot_transport(allgather, user, nranks, rank));
+   }
+   *ctx = h.release();
+   D2D_CATCH
+}
+
 int d2d_group_create(d2d_group **grp, int nranks)
 {
    D2D_TRY
@@ -120,8 +133,7 @@ int d2d_ctx_destroy(d2d_ctx *ctx)
 int d2d_ctx_sync(d2d_ctx *ctx)
 {
    D2D_TRY
-   D2D_CHECK_CUDA(cudaSetDevice(ctx->c.device));
-   D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+   ctx->c.sync_all();
    D2D_CATCH
 }
 int d2d_ctx_set_blocking(d2d_ctx *ctx, int blocking)

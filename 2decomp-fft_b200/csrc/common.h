@@ -39,8 +39,8 @@ const std::string &get_last_error();
 
 constexpr int kMaxP = kMaxPieces; // max ranks along one side of the process grid
 constexpr int kMaxRanks = kMaxPieces * kMaxPieces;
-constexpr int kWorkBuffers = 3;  // rotated by the chains and mapped between ranks (p2p.cpp)
-constexpr int kCtxBuffers = 4;   // + one more for the overlapped chain on two-dimensional process grids (never mapped)
+constexpr int kCtxBuffers = 4;   // link s of a chain: send buffer 2 s, receive buffer 2 s + 1 (pipelined chains); rotated otherwise
+constexpr int kWorkBuffers = kCtxBuffers; // all of them are mapped between the ranks (p2p.cpp)
 
 // decomp_info (src/info.f90:19-47).  0-based starts internally; the C ABI converts to 1-based.
 struct Decomp {
@@ -81,6 +81,9 @@ struct Transport {
 };
 
 Transport *make_nccl_transport(const unsigned char id[128], int nranks, int rank);
+// bootstrap-only transport: the caller supplies the all-gather (MPI_Allgather in the Fortran shim, torch.distributed in the
+// Python mirror); the data plane is the peer-memory path of p2p.cpp (copy engines / peer stores over NVLink), no NCCL
+Transport *make_boot_transport(d2d_allgather_fn fn, void *user, int nranks, int rank);
 void nccl_unique_id(unsigned char id[128]);
 struct Group;
 Group *group_create(int nranks);
@@ -105,9 +108,18 @@ struct Ctx {
    void *work[kCtxBuffers] = {nullptr, nullptr, nullptr, nullptr};
    size_t work_bytes[kCtxBuffers] = {0, 0, 0, 0};
    struct P2P *p2p = nullptr; // peer-mapped work buffers + flags (p2p.cpp); null when unused
-   // chunk-wise overlapped chains (fft_plan.cpp run_chain_overlap): the exchanges run on their own stream
+   // chunk-wise pipelined chains (fft_plan.cpp run_chain_pipe): the exchanges run on their own streams -- one per peer
+   // of a communicator for the copy-engine pushes of the peer-memory path, comm_stream for the transports' exchanges
    cudaStream_t comm_stream = nullptr;
-   std::vector<cudaEvent_t> sync_events; // untimed events ordering the two streams, reused between calls
+   cudaStream_t copy_stream[kMaxP] = {};
+   cudaStream_t io_stream[2] = {}; // host-array entry points: [0] uploads (H2D), [1] downloads (D2H)
+   std::vector<cudaEvent_t> sync_events; // untimed events ordering the streams, reused between calls
+   size_t next_sync_event = 0;
+   std::vector<cudaEvent_t> buf_busy[kCtxBuffers]; // copies still reading work[w] (recorded on the copy streams)
+   cudaStream_t copy_stream_for(int k);
+   cudaEvent_t new_sync_event();
+   void wait_buffer_idle(int w, cudaStream_t st); // st waits for the copies that read work[w]
+   void mark_buffer_busy(int w, int nstreams);    // record the current tail of copy streams 0..nstreams-1 against work[w]
    // profiling
    bool profiling = false;
    std::vector<ProfEntry> prof;
@@ -119,14 +131,31 @@ struct Ctx {
    std::vector<cudaEvent_t> event_pool;
 
    void *reserve(int which, size_t bytes);
-   void prof_begin(const char *label, double bytes, Pending &p);
-   void prof_end(Pending &p);
+   // Collective over the ranks of the context: grow work[0..nbuf) to at least `bytes` (a size every rank computes
+   // identically) and (re)publish them to the peers when anything changed -- peers hold mappings of these buffers, so they
+   // are never resized by one rank alone.
+   void ensure_buffers(int nbuf, size_t bytes, bool force_publish);
+   bool published = false;
+   void prof_begin(const char *label, double bytes, Pending &p, cudaStream_t st = nullptr);
+   void prof_end(Pending &p, cudaStream_t st = nullptr);
    void prof_flush();
    int peer_rank_col(int m) const { return m * p_col + c2; } // COL communicator: same coord(2), index = coord(1)
    int peer_rank_row(int m) const { return c1 * p_col + m; } // ROW communicator: same coord(1), index = coord(2)
+   // host-memory dependencies between the host-array entry points (fft_plan.cpp fft_3d_host)
+   struct HostTrack {
+      static constexpr size_t kMaxPieces = 72;
+      const char *d2h_base = nullptr; // host range the most recent download writes, in pieces [first, second) with one event each
+      size_t d2h_bytes = 0;
+      std::vector<std::pair<size_t, size_t>> d2h_cut;
+      cudaEvent_t d2h_ev[kMaxPieces] = {};
+      const char *h2d_base = nullptr; // host range the most recent upload reads
+      size_t h2d_bytes = 0;
+      cudaEvent_t h2d_done = nullptr;
+   } host;
+   void sync_all(); // every stream of the context
    void finish_call()
    {
-      if (blocking) D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+      if (blocking) sync_all();
    }
    ~Ctx();
 };
@@ -135,13 +164,14 @@ struct ProfScope {
    Ctx *c;
    Ctx::Pending p{};
    bool on;
-   ProfScope(Ctx *ctx, const char *label, double bytes = 0) : c(ctx), on(ctx->profiling)
+   cudaStream_t st;
+   ProfScope(Ctx *ctx, const char *label, double bytes = 0, cudaStream_t stream = nullptr) : c(ctx), on(ctx->profiling), st(stream)
    {
-      if (on) c->prof_begin(label, bytes, p);
+      if (on) c->prof_begin(label, bytes, p, st);
    }
    ~ProfScope()
    {
-      if (on) c->prof_end(p);
+      if (on) c->prof_end(p, st);
    }
 };
 
@@ -166,7 +196,10 @@ PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es);
 // recv-side map for pencil `to` fed from pencil `from`: peers' blocks in recvbuf, own block in sendbuf
 PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es);
 // the exchange itself (peers other than self); element size es
-void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es);
+// send_w / recv_w: indices of the context's work buffers holding sendbuf / recvbuf (-1: a user array); the peer-memory
+// path needs recvbuf == work[recv_w]
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w);
+size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es); // largest pencil of any rank of the grid, in bytes
 int64_t send_total(const Decomp &d, int from, int to);
 int64_t recv_total(const Decomp &d, int from, int to);
 int comm_size(const Decomp &d, int from, int to);
@@ -193,14 +226,20 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
 
 // peer-memory path of the fused transforms (p2p.cpp)
 void p2p_publish(Ctx *ctx);
+void p2p_unpublish(Ctx *ctx); // collective: close the mappings of the peers' work buffers (before they are reallocated)
 void p2p_destroy(struct P2P *p);
 bool p2p_active(const Ctx *ctx);
 void p2p_invalidate(Ctx *ctx);
 void *p2p_peer_work(const Ctx *ctx, int w, int rank);
 size_t p2p_peer_bytes(const Ctx *ctx, int w, int rank);
 uint32_t p2p_next_epoch(Ctx *ctx);
-void p2p_signal(Ctx *ctx, int peer, int which, uint32_t epoch);
-void p2p_wait(Ctx *ctx, int peer, int which, uint32_t epoch);
+uint32_t p2p_reserve_seq(Ctx *ctx, uint32_t n); // n consecutive chunk sequence numbers; returns the number before the first
+// flags `which`: 0 ready (epochs), 1 done (epochs of the fused chain), 2 arrived (chunk sequence numbers of the pipelined chain)
+void p2p_signal(Ctx *ctx, int peer, int which, uint32_t value, cudaStream_t st = nullptr);
+void p2p_wait(Ctx *ctx, int peer, int which, uint32_t value, cudaStream_t st = nullptr);
+// all-to-all(v) over peer memory for the bare transposes: every PeerXfer's recvptr must lie in work[recv_w] (the peers push
+// into the same offsets of their peers' work[recv_w]); dst_off[i] = byte offset in the DESTINATION rank's work[recv_w]
+void p2p_exchange(Ctx *ctx, const std::vector<PeerXfer> &xf, const std::vector<size_t> &dst_off, int recv_w, int send_w);
 
 } // namespace d2d
 

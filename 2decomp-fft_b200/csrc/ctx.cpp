@@ -111,7 +111,69 @@ void *Ctx::reserve(int which, size_t bytes)
    return work[which];
 }
 
-void Ctx::prof_begin(const char *label, double bytes, Pending &p)
+void Ctx::sync_all()
+{
+   D2D_CHECK_CUDA(cudaSetDevice(device));
+   D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+   if (comm_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(comm_stream));
+   for (int k = 0; k < kMaxP; k++)
+      if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
+   for (cudaStream_t s : io_stream)
+      if (s) D2D_CHECK_CUDA(cudaStreamSynchronize(s));
+}
+
+cudaStream_t Ctx::copy_stream_for(int k)
+{
+   D2D_REQUIRE(k >= 0 && k < kMaxP, "copy stream index out of range");
+   if (!copy_stream[k]) D2D_CHECK_CUDA(cudaStreamCreateWithFlags(&copy_stream[k], cudaStreamNonBlocking));
+   return copy_stream[k];
+}
+
+cudaEvent_t Ctx::new_sync_event()
+{
+   // a ring: an event is re-recorded only long after the waits that referred to its previous record were enqueued (a
+   // wait captures the record that is current when it is enqueued, so re-recording never disturbs it)
+   if (sync_events.size() < 512) {
+      cudaEvent_t e;
+      D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      sync_events.push_back(e);
+      return e;
+   }
+   return sync_events[next_sync_event++ % sync_events.size()];
+}
+
+void Ctx::wait_buffer_idle(int w, cudaStream_t st)
+{
+   for (cudaEvent_t e : buf_busy[w]) D2D_CHECK_CUDA(cudaStreamWaitEvent(st, e, 0));
+}
+
+void Ctx::mark_buffer_busy(int w, int nstreams)
+{
+   while ((int)buf_busy[w].size() < nstreams) {
+      cudaEvent_t e;
+      D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      buf_busy[w].push_back(e);
+   }
+   for (int k = 0; k < nstreams; k++) D2D_CHECK_CUDA(cudaEventRecord(buf_busy[w][k], copy_stream_for(k)));
+}
+
+void Ctx::ensure_buffers(int nbuf, size_t bytes, bool force_publish)
+{
+   bool grow = false;
+   for (int i = 0; i < nbuf; i++) grow = grow || work_bytes[i] < bytes;
+   if (!grow && !force_publish && published) return;
+   if (grow) {
+      // nobody may still be copying out of / into the old buffers
+      for (int k = 0; k < kMaxP; k++)
+         if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
+      p2p_unpublish(this); // collective: every rank closes its mappings of the peers' buffers before anybody frees one
+      for (int i = 0; i < nbuf; i++) reserve(i, bytes);
+   }
+   p2p_publish(this); // collective (no-op for a single rank / in-process groups)
+   published = true;
+}
+
+void Ctx::prof_begin(const char *label, double bytes, Pending &p, cudaStream_t st)
 {
    int idx = -1;
    for (size_t i = 0; i < prof.size(); i++)
@@ -130,17 +192,20 @@ void Ctx::prof_begin(const char *label, double bytes, Pending &p)
    p.idx = idx;
    p.a = get_event();
    p.b = get_event();
-   D2D_CHECK_CUDA(cudaEventRecord(p.a, stream));
+   D2D_CHECK_CUDA(cudaEventRecord(p.a, st ? st : stream));
 }
-void Ctx::prof_end(Pending &p)
+void Ctx::prof_end(Pending &p, cudaStream_t st)
 {
-   cudaEventRecord(p.b, stream);
+   cudaEventRecord(p.b, st ? st : stream);
    pending.push_back(p);
 }
 void Ctx::prof_flush()
 {
    if (pending.empty()) return;
    D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
+   if (comm_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(comm_stream));
+   for (int k = 0; k < kMaxP; k++)
+      if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
    for (auto &p : pending) {
       float ms = 0;
       D2D_CHECK_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
@@ -160,7 +225,16 @@ Ctx::~Ctx()
    p2p = nullptr;
    tr.reset();
    if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
+   for (int k = 0; k < kMaxP; k++)
+      if (copy_stream[k]) { cudaStreamSynchronize(copy_stream[k]); cudaStreamDestroy(copy_stream[k]); }
+   for (cudaStream_t s : io_stream)
+      if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+   for (auto e : host.d2h_ev)
+      if (e) cudaEventDestroy(e);
+   if (host.h2d_done) cudaEventDestroy(host.h2d_done);
    for (auto e : sync_events) cudaEventDestroy(e);
+   for (auto &v : buf_busy)
+      for (auto e : v) cudaEventDestroy(e);
    for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
    for (auto e : event_pool) cudaEventDestroy(e);
    for (int i = 0; i < kCtxBuffers; i++)
@@ -233,5 +307,32 @@ struct LocalTransport : Transport {
 };
 } // namespace
 Transport *make_local_transport(Group *g, int rank) { return new LocalTransport(g, rank); }
+
+// ---- bootstrap-only transport: the caller's all-gather (MPI / torch.distributed), no data plane of its own ----------
+namespace {
+struct BootTransport : Transport {
+   d2d_allgather_fn fn;
+   void *user;
+   int nranks, rank;
+   BootTransport(d2d_allgather_fn f, void *u, int n, int r) : fn(f), user(u), nranks(n), rank(r) {}
+   int kind() const override { return D2D_TRANSPORT_BOOT; }
+   void exchange(const std::vector<PeerXfer> &, cudaStream_t) override
+   {
+      D2D_REQUIRE(false, "bootstrap transport: the exchange needs the peer-memory path (CUDA IPC between the ranks' devices), which is not active");
+   }
+   void allgather(const void *send_host, void *recv_host, size_t bytes, cudaStream_t) override
+   {
+      D2D_REQUIRE(fn(user, send_host, recv_host, (int64_t)bytes) == 0, "bootstrap all-gather callback failed");
+   }
+   void barrier(cudaStream_t st) override
+   {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(st));
+      std::vector<char> r(nranks);
+      char s = 0;
+      allgather(&s, r.data(), 1, st);
+   }
+};
+} // namespace
+Transport *make_boot_transport(d2d_allgather_fn fn, void *user, int nranks, int rank) { return new BootTransport(fn, user, nranks, rank); }
 
 } // namespace d2d

@@ -317,7 +317,7 @@ void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendb
 
 // all-to-all(v) with the peers of the row / column communicator (self excluded).
 // Replaces decomp_2d_nccl_alltoall_{col,row}_* (src/decomp_2d_nccl.f90:214-473) / MPI_ALLTOALLV.
-void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es)
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w)
 {
    const bool col = (from == 0 || to == 0);
    const int np = col ? d.p_row : d.p_col;
@@ -325,7 +325,9 @@ void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, 
    if (np == 1) return;
    D2D_REQUIRE(ctx->tr != nullptr, "context has no transport but the process grid has more than one rank");
    const Side s = side_of(d, from, to), r = side_of(d, to, from);
+   const bool p2p = p2p_active(ctx);
    std::vector<PeerXfer> xf;
+   std::vector<size_t> dst_off;
    double bytes = 0;
    for (int k = 1; k < np; k++) {
       const int m = (me + k) % np; // stagger the peers
@@ -337,10 +339,33 @@ void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, 
       x.recvbytes = (size_t)es * r.cnts[m];
       bytes += (double)x.sendbytes;
       xf.push_back(x);
+      if (p2p) { // where the destination rank expects the block from this rank
+         Decomp dm;
+         decomp_init(dm, d.nx, d.ny, d.nz, d.p_row, d.p_col, x.peer);
+         const Side rm = side_of(dm, to, from);
+         D2D_REQUIRE(rm.cnts[me] == s.cnts[m], "exchange: block sizes of the two sides disagree");
+         dst_off.push_back((size_t)es * rm.disp[me]);
+      }
    }
    static const char *names[3][3] = {{"", "a2a_x_y", ""}, {"a2a_y_x", "", "a2a_y_z"}, {"", "a2a_z_y", ""}};
    ProfScope ps(ctx, names[from][to], bytes);
-   ctx->tr->exchange(xf, ctx->stream);
+   if (p2p) {
+      D2D_REQUIRE(recv_w >= 0 && recvbuf == ctx->work[recv_w], "peer-memory exchange: the receive side must be a work buffer");
+      p2p_exchange(ctx, xf, dst_off, recv_w, send_w);
+   } else {
+      ctx->tr->exchange(xf, ctx->stream);
+   }
+}
+
+size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es)
+{
+   int64_t m = 0;
+   for (int r = 0; r < ctx->nranks; r++) {
+      Decomp a;
+      decomp_init(a, d.nx, d.ny, d.nz, ctx->p_row, ctx->p_col, r);
+      m = std::max(m, a.max_pencil());
+   }
+   return (size_t)es * (size_t)m;
 }
 
 } // namespace d2d

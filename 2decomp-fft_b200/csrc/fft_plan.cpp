@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "common.h"
 #include "fft_registry.h"
@@ -17,14 +18,28 @@ namespace d2d {
 bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_t *err);
 cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode); // fft_any.cu: lengths without a compiled kernel
 
+// Gates between the host-array entry points and the chains: the user's input arrives over PCIe in pieces and the
+// output leaves in pieces.  A user X-pencil is contiguous in z-slabs, and z is a batch axis of the x stage, so a first /
+// last stage on the X-pencil runs slab by slab as the slabs arrive / leaves slab by slab as they are produced.
+struct IoGate {
+   int nio = 8;                                    // slabs of an x stage that would otherwise run whole
+   std::function<void(size_t, size_t)> need_in;   // the compute stream must not read bytes [lo, hi) of `in` before they arrived
+   std::function<void(size_t, size_t)> have_out;  // bytes [lo, hi) of `out` are final once the work enqueued so far has run
+};
+
 struct Plan {
    Ctx *ctx;
    int format, nx, ny, nz, f64, inplace;
    int skip[3];
    d2d_decomp ph, sp;
-   // device staging for the *_host entry points
-   void *stage_in = nullptr, *stage_out = nullptr;
-   size_t stage_in_bytes = 0, stage_out_bytes = 0;
+   // device staging for the *_host entry points: one (in, out) pair per kind of transform (0 r2c, 1 c2r, 2 c2c) so that
+   // consecutive calls overlap (the download of one call with the upload of the next)
+   struct HostIo {
+      void *in = nullptr, *out = nullptr;
+      size_t in_bytes = 0, out_bytes = 0;
+      cudaEvent_t in_done = nullptr, out_done = nullptr; // last compute that read `in` / last download that read `out`
+   } io[3];
+   const IoGate *gate = nullptr; // set around a chain by fft_3d_host
 };
 
 static const int *pencil_size(const Decomp &d, int p) { return p == 0 ? d.xsz : p == 1 ? d.ysz : d.zsz; }
@@ -122,6 +137,39 @@ struct StageDef {
    int pencil, mode;
 };
 
+// Stage s of a chain, with the host-array gates: an x stage that reads the user's input (s == 0) or writes the user's
+// output (s == 2) runs slab by slab along z (batch axis b), waiting for / announcing the byte range of each slab.
+static void run_chain_stage(Plan &p, int s, int mode, int pencil, const Decomp &dc, const Decomp *dr, const PieceMap &in, const PieceMap &out,
+                            void *rptr, int backward, int passthrough, StageRange rg = StageRange())
+{
+   Ctx *ctx = p.ctx;
+   const IoGate *g = p.gate;
+   const bool gin = g && g->need_in && s == 0 && pencil == 0;
+   const bool gout = g && g->have_out && s == 2 && pencil == 0;
+   if (!gin && !gout) return run_stage(ctx, p.f64, mode, pencil, dc, dr, in, out, rptr, backward, passthrough, true, rg);
+   D2D_REQUIRE(rg.axis != 0, "an x stage is chunked along z only");
+   const int rs = p.f64 ? 8 : 4;
+   const Decomp &di = (mode == MODE_R2C) ? *dr : dc, &dq = (mode == MODE_C2R) ? *dr : dc;
+   const size_t plane_in = (size_t)(mode == MODE_R2C ? rs : 2 * rs) * di.xsz[0] * di.xsz[1];
+   const size_t plane_out = (size_t)(mode == MODE_C2R ? rs : 2 * rs) * dq.xsz[0] * dq.xsz[1];
+   int na = 0, nb = 0;
+   fft_stage_batch(dc, pencil, na, nb);
+   std::vector<int> cut;
+   if (rg.axis == 1) { cut.push_back(rg.f0); cut.push_back(rg.f1); }
+   else {
+      const int k = std::max(1, std::min(g->nio, nb));
+      for (int c = 0; c <= k; c++) cut.push_back((int)((long long)nb * c / k));
+   }
+   for (size_t c = 0; c + 1 < cut.size(); c++) {
+      if (cut[c] == cut[c + 1]) continue;
+      if (gin) g->need_in(plane_in * cut[c], plane_in * cut[c + 1]);
+      StageRange r;
+      r.axis = 1; r.f0 = cut[c]; r.f1 = cut[c + 1];
+      run_stage(ctx, p.f64, mode, pencil, dc, dr, in, out, rptr, backward, passthrough, true, r);
+      if (gout) g->have_out(plane_out * cut[c], plane_out * cut[c + 1]);
+   }
+}
+
 // Generic 3-stage chain.  `in`/`out` are the user arrays (dense pencils); exactly one of them is real
 // for r2c/c2r.  Between two stages the data lives in a work buffer in the private wire layout of
 // that link (decomp.cpp): the producer writes its send blocks (the block it keeps for itself
@@ -132,146 +180,194 @@ struct StageDef {
 static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward);
 static size_t uniform_work_bytes(const Plan &p, bool c2c);
 
-// ---- chunk-wise overlap of the exchanges with their neighbouring stages (opt-in: D2D_OVERLAP=<chunks>, NCCL / in-process
-// transports) ---------------------------------------------------------------------------------------------------------
-// Every link with more than one rank is cut into K chunks along its free axis (fft_link_chunk: contiguous sub-ranges of
-// every block).  The producer runs chunk by chunk on the context's stream; as soon as chunk c is written its sub-ranges are
-// exchanged on the communication stream while the producer works on chunk c + 1.  The consumer of a link follows chunk by
-// chunk as the exchanges complete -- unless it is itself the chunked producer of the next link (the middle stage of a
-// p_row > 1, p_col > 1 grid: its input chunks run along x, its output chunks along z), in which case it starts after the
-// last chunk of its input has arrived.  Work-buffer rotation and maps are those of run_chain.
-static int overlap_chunks()
+// ---- chunk-wise pipelining of the exchanges with their neighbouring stages ---------------------------------------------
+// The default of every multi-rank chain.  Every link with more than one rank is cut into K chunks along its free axis
+// (fft_link_chunk: contiguous sub-ranges of every block).  The producer runs chunk by chunk on the context's stream at HBM
+// speed into a local send buffer (its own block included: that one never moves); as soon as chunk c is written its
+// sub-ranges travel while the producer works on chunk c + 1, and the consumer of the link follows chunk by chunk as they
+// land -- unless it is itself the chunked producer of the next link (the middle stage of a p_row > 1, p_col > 1 grid: its
+// input chunks run along x, its output chunks along z), in which case it starts after the last chunk of its input.
+//
+// Two data planes:
+//  * peer memory (default with one process per GPU): the COPY ENGINES push every sub-range straight into the destination
+//    rank's receive buffer over NVLink (CUDA-IPC mapped, p2p.cpp), one copy stream per peer, so the SMs only ever run
+//    HBM-bound FFT kernels and the link runs at the DMA rate while they compute.  Ranks are ordered by stream-ordered
+//    flags: ready (epoch e: the destination is done with the previous contents of its receive buffer; waited for by the
+//    copy stream, never by the compute stream) and arrived (chunk sequence number: the sub-range has landed; waited for by
+//    the consumer).  No host synchronisation, no SMs spent on communication, no NCCL.
+//  * a transport (NCCL grouped send/recv with D2D_P2P=0, or the in-process transport of the thread-per-rank groups): the
+//    same pipeline with the chunk exchanges on a communication stream, ordered by events.
+// Replaces the pack -> all-to-all -> host sync -> unpack sequence of the reference (src/decomp_2d_nccl.f90:214-252 and the
+// cudaStreamSynchronize at :249, :324, :395, :470).  Link s uses work buffer 2 s as send and 2 s + 1 as receive buffer.
+static int pipe_chunks()
 {
-   const char *v = getenv("D2D_OVERLAP"); // read per call: tests switch it at run time
-   const int k = v ? atoi(v) : 0;
-   return k > 64 ? 64 : k;
+   const char *v = getenv("D2D_CHUNKS"); // read per call: tests switch it at run time
+   if (!v) v = getenv("D2D_OVERLAP");    // round-1 name
+   const int k = v ? atoi(v) : 4;
+   return k > 64 ? 64 : k < 1 ? 1 : k;
 }
 
-static void run_chain_overlap(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward, int K)
+static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward, int K)
 {
    Ctx *ctx = p.ctx;
    const int es = p.f64 ? 16 : 8;
    const int padq = 128 / es;
    const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
-   if (!ctx->comm_stream) D2D_CHECK_CUDA(cudaStreamCreate(&ctx->comm_stream));
-   size_t next_event = 0;
-   auto new_event = [&]() {
-      if (next_event == ctx->sync_events.size()) {
-         cudaEvent_t e;
-         D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-         ctx->sync_events.push_back(e);
-      }
-      return ctx->sync_events[next_event++];
-   };
+   const bool ce = p2p_active(ctx);
+   if (!ce && !ctx->comm_stream) D2D_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
    const bool real_link[2] = {comm_size(dc, st[0].pencil, st[1].pencil) > 1, comm_size(dc, st[1].pencil, st[2].pencil) > 1};
    // chunk boundaries of a link: K pieces of the free axis, cut on multiples of 16 lines (tiles and real pairs stay whole)
    // Always K chunks (empty ones allowed): every rank of the grid then issues the same number of exchanges whatever its
-   // own extents are, which the in-process transport (one barrier over all ranks per exchange) relies on.
+   // own extents are, which the in-process transport (one barrier over all ranks per exchange) and the chunk sequence
+   // numbers of the peer-memory path rely on.
    auto bounds = [&](int nf) {
       std::vector<int> b(K + 1, 0);
       for (int c = 1; c < K; c++) b[c] = std::max(b[c - 1], (int)((long long)nf * c / K) / 16 * 16);
       b[K] = nf;
       return b;
    };
-   // work buffers holding the current stage's input (self block / received blocks).  A chunked producer still reads them
-   // while its first chunks are being exchanged, so it needs two MORE buffers (send, receive): four on a 2-D process grid.
-   int live_a = -1, live_b = -1;
-   auto pick = [&](int avoid) {
-      for (int i = 0; i < kCtxBuffers; i++)
-         if (i != live_a && i != live_b && i != avoid) return i;
-      return -1;
-   };
+   for (int w = 0; w < kCtxBuffers; w++) D2D_REQUIRE(ctx->work_bytes[w] >= wbytes, "pipelined chain: work buffers were not reserved");
    PieceMap cur = fft_user_map(dc, st[0].pencil, in);
-   std::vector<cudaEvent_t> arrived;       // per chunk of the link feeding the current stage: its exchange has completed
-   std::vector<int> arrived_bounds;        // chunk boundaries of that link
+   // the link feeding the current stage
+   struct Feed {
+      bool chunked = false;
+      std::vector<int> bounds;
+      std::vector<cudaEvent_t> arrived; // transport plane: the exchange of chunk c has completed
+      uint32_t seq_base = 0;            // peer-memory plane: chunk c has landed when arrived_from[peer] >= seq_base + c + 1
+      std::vector<int> peers;           // global ranks of the peers of the link
+   } feed;
+   auto wait_chunk = [&](int c) {
+      ProfScope ps(ctx, "pipe_wait");
+      if (ce) for (int r : feed.peers) p2p_wait(ctx, r, 2, feed.seq_base + (uint32_t)c + 1);
+      else D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, feed.arrived[c], 0));
+   };
    for (int s = 0; s < 3; s++) {
       const int pen = st[s].pencil, mode = st[s].mode;
       const bool last = (s == 2);
       const int passthrough = (mode == MODE_C2C && p.skip[pen]) ? 1 : 0;
       PieceMap om{};
       void *rptr = nullptr, *sendbuf = nullptr;
-      int send_w = -1;
+      const int send_w = 2 * s, recv_w = 2 * s + 1;
       if (mode == MODE_R2C) rptr = in;
       if (last) {
          if (mode == MODE_C2R) rptr = out;
          else om = fft_user_map(dc, pen, out);
       } else {
-         send_w = pick(-1);
-         sendbuf = ctx->reserve(send_w, wbytes);
+         ctx->wait_buffer_idle(send_w, ctx->stream); // earlier pushes out of this buffer
+         sendbuf = ctx->work[send_w];
          om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false, padq);
       }
       const bool produce_chunked = !last && real_link[s];
-      const bool consume_chunked = !arrived.empty() && !produce_chunked;
-      void *recvbuf = nullptr;
-      int recv_w = -1;
       if (produce_chunked) {
          const int nxt = st[s + 1].pencil;
-         recv_w = pick(send_w);
-         D2D_REQUIRE(recv_w >= 0 && recv_w != send_w, "overlapped chain: no free work buffer");
-         recvbuf = ctx->reserve(recv_w, wbytes);
-         if (!arrived.empty()) { // the whole input must be here before the first chunk
-            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived.back(), 0));
-            arrived.clear();
+         void *recvbuf = ctx->work[recv_w];
+         if (feed.chunked) { // the whole input must be here before the first chunk
+            wait_chunk((int)feed.bounds.size() - 2);
+            feed = Feed();
          }
          LinkChunk probe;
          fft_link_chunk(dc, pen, nxt, padq, 0, 0, probe);
          const std::vector<int> b = bounds(probe.nf);
-         std::vector<cudaEvent_t> done;
          const bool col = (pen == 0 || nxt == 0);
-         for (size_t c = 0; c + 1 < b.size(); c++) {
+         const int np = probe.np, me = probe.me;
+         Feed nf;
+         nf.chunked = true;
+         nf.bounds = b;
+         std::vector<Decomp> dpeer(np);
+         for (int k = 1; k < np; k++) {
+            const int m = (me + k) % np;
+            const int prank = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
+            nf.peers.push_back(prank);
+            if (ce) decomp_init(dpeer[m], dc.nx, dc.ny, dc.nz, ctx->p_row, ctx->p_col, prank);
+         }
+         uint32_t epoch = 0;
+         static const char *names[3][3] = {{"", "ce_x_y", ""}, {"ce_y_x", "", "ce_y_z"}, {"", "ce_z_y", ""}};
+         std::vector<Ctx::Pending> spans(np);
+         if (ce) {
+            epoch = p2p_next_epoch(ctx);
+            nf.seq_base = p2p_reserve_seq(ctx, (uint32_t)K);
+            for (int r : nf.peers) p2p_signal(ctx, r, 0, epoch); // stream order: this rank is done with the old contents of work[recv_w]
+         }
+         for (int c = 0; c < K; c++) {
             StageRange rg;
             rg.axis = probe.axis_is_a ? 0 : 1; rg.f0 = b[c]; rg.f1 = b[c + 1];
-            run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true, rg);
-            cudaEvent_t written = new_event();
+            run_chain_stage(p, s, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, rg);
+            cudaEvent_t written = ctx->new_sync_event();
             D2D_CHECK_CUDA(cudaEventRecord(written, ctx->stream));
-            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, written, 0));
-            LinkChunk S, R;
+            LinkChunk S;
             fft_link_chunk(dc, pen, nxt, padq, b[c], b[c + 1], S);
-            fft_link_chunk(dc, nxt, pen, padq, b[c], b[c + 1], R);
-            std::vector<PeerXfer> xf;
-            for (int k = 1; k < S.np; k++) {
-               const int m = (S.me + k) % S.np;
-               PeerXfer x;
-               x.peer = col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m);
-               x.sendptr = (const char *)sendbuf + (size_t)es * S.off[m];
-               x.sendbytes = (size_t)es * S.cnt[m];
-               x.recvptr = (char *)recvbuf + (size_t)es * R.off[m];
-               x.recvbytes = (size_t)es * R.cnt[m];
-               xf.push_back(x);
+            if (ce) {
+               for (int k = 1; k < np; k++) {
+                  const int m = (me + k) % np;
+                  const int prank = nf.peers[k - 1];
+                  cudaStream_t cs = ctx->copy_stream_for(k - 1);
+                  LinkChunk R; // the consumer side ON THE DESTINATION rank: where it expects this rank's block
+                  fft_link_chunk(dpeer[m], nxt, pen, padq, b[c], b[c + 1], R);
+                  D2D_REQUIRE(R.cnt[me] == S.cnt[m], "pipelined chain: chunk sizes of the two sides disagree");
+                  D2D_CHECK_CUDA(cudaStreamWaitEvent(cs, written, 0));
+                  if (c == 0) {
+                     p2p_wait(ctx, prank, 0, epoch, cs);
+                     if (ctx->profiling) ctx->prof_begin(names[pen][nxt], 0, spans[k], cs);
+                  }
+                  char *dst = (char *)p2p_peer_work(ctx, recv_w, prank);
+                  const size_t off = (size_t)es * R.off[me], nbytes = (size_t)es * S.cnt[m];
+                  D2D_REQUIRE(dst != nullptr && off + nbytes <= p2p_peer_bytes(ctx, recv_w, prank), "pipelined chain: destination buffer too small");
+                  if (nbytes) D2D_CHECK_CUDA(cudaMemcpyAsync(dst + off, (const char *)sendbuf + (size_t)es * S.off[m], nbytes, cudaMemcpyDefault, cs));
+                  p2p_signal(ctx, prank, 2, nf.seq_base + (uint32_t)c + 1, cs);
+                  if (ctx->profiling) {
+                     ctx->prof[spans[k].idx].bytes += (double)nbytes;
+                     if (c == K - 1) ctx->prof_end(spans[k], cs);
+                  }
+               }
+            } else {
+               D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, written, 0));
+               LinkChunk R;
+               fft_link_chunk(dc, nxt, pen, padq, b[c], b[c + 1], R);
+               std::vector<PeerXfer> xf;
+               for (int k = 1; k < np; k++) {
+                  const int m = (me + k) % np;
+                  PeerXfer x;
+                  x.peer = nf.peers[k - 1];
+                  x.sendptr = (const char *)sendbuf + (size_t)es * S.off[m];
+                  x.sendbytes = (size_t)es * S.cnt[m];
+                  x.recvptr = (char *)recvbuf + (size_t)es * R.off[m];
+                  x.recvbytes = (size_t)es * R.cnt[m];
+                  xf.push_back(x);
+               }
+               ctx->tr->exchange(xf, ctx->comm_stream);
+               cudaEvent_t e = ctx->new_sync_event();
+               D2D_CHECK_CUDA(cudaEventRecord(e, ctx->comm_stream));
+               nf.arrived.push_back(e);
             }
-            ctx->tr->exchange(xf, ctx->comm_stream);
-            cudaEvent_t e = new_event();
-            D2D_CHECK_CUDA(cudaEventRecord(e, ctx->comm_stream));
-            done.push_back(e);
          }
-         arrived = done;
-         arrived_bounds = b;
-         live_a = send_w;
-         live_b = recv_w;
+         if (ce) ctx->mark_buffer_busy(send_w, np - 1);
+         else { // the communication stream still reads the send buffer: the next writer of it waits for that
+            if (ctx->buf_busy[send_w].empty()) {
+               cudaEvent_t e;
+               D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+               ctx->buf_busy[send_w].push_back(e);
+            }
+            D2D_CHECK_CUDA(cudaEventRecord(ctx->buf_busy[send_w][0], ctx->comm_stream));
+         }
+         feed = nf;
          cur = fft_link_map(dc, nxt, pen, recvbuf, sendbuf, es, true, padq);
          continue;
       }
-      if (consume_chunked) { // chunk by chunk as the exchanges of the feeding link complete (same free axis, seen from this side)
+      if (feed.chunked) { // chunk by chunk as the sub-ranges of the feeding link land (same free axis, seen from this side)
          LinkChunk probe;
          fft_link_chunk(dc, pen, st[s - 1].pencil, padq, 0, 0, probe);
-         for (size_t c = 0; c + 1 < arrived_bounds.size(); c++) {
-            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived[c], 0));
+         for (size_t c = 0; c + 1 < feed.bounds.size(); c++) {
+            wait_chunk((int)c);
             StageRange rg;
-            rg.axis = probe.axis_is_a ? 0 : 1; rg.f0 = arrived_bounds[c]; rg.f1 = arrived_bounds[c + 1];
-            run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true, rg);
+            rg.axis = probe.axis_is_a ? 0 : 1; rg.f0 = feed.bounds[c]; rg.f1 = feed.bounds[c + 1];
+            run_chain_stage(p, s, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, rg);
          }
-         arrived.clear();
+         feed = Feed();
       } else {
-         if (!arrived.empty()) {
-            D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, arrived.back(), 0));
-            arrived.clear();
-         }
-         run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+         run_chain_stage(p, s, mode, pen, dc, dr, cur, om, rptr, backward, passthrough);
       }
       if (last) break;
       // a link inside one rank: the consumer reads what this stage wrote
-      live_a = send_w;
-      live_b = -1;
       cur = fft_link_map(dc, st[s + 1].pencil, pen, nullptr, sendbuf, es, true, padq);
    }
 }
@@ -279,8 +375,14 @@ static void run_chain_overlap(Plan &p, const Decomp &dc, const Decomp *dr, const
 static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
    Ctx *ctx = p.ctx;
-   if (p2p_active(ctx)) return run_chain_p2p(p, dc, dr, st, in, out, backward);
-   if (overlap_chunks() > 1 && ctx->nranks > 1) return run_chain_overlap(p, dc, dr, st, in, out, backward, overlap_chunks());
+   // multi-rank: the chunk-pipelined chain (copy-engine pushes over peer memory, or the transport's exchange); D2D_FUSED=1
+   // selects the round-1 variant whose producer kernels store straight into the peers' buffers (no chunks, no copy engines),
+   // D2D_CHUNKS=0 the plain stage -> exchange -> stage sequence on the transport
+   static const bool fused = getenv("D2D_FUSED") && atoi(getenv("D2D_FUSED")) != 0;
+   if (p2p_active(ctx) && fused) return run_chain_p2p(p, dc, dr, st, in, out, backward);
+   const char *ck = getenv("D2D_CHUNKS") ? getenv("D2D_CHUNKS") : getenv("D2D_OVERLAP");
+   const bool plain = ck && atoi(ck) <= 0;
+   if (ctx->nranks > 1 && (p2p_active(ctx) || !plain)) return run_chain_pipe(p, dc, dr, st, in, out, backward, pipe_chunks());
    const int es = p.f64 ? 16 : 8;
    const int padq = 128 / es;
    const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
@@ -309,7 +411,7 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
          else { send_w = pick(); sendbuf = ctx->reserve(send_w, wbytes); }
          om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false, padq);
       }
-      run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+      run_chain_stage(p, s, mode, pen, dc, dr, cur, om, rptr, backward, passthrough);
       if (last) break;
       const int nxt = st[s + 1].pencil;
       // the input buffers of this stage are free once it has run (stream order)
@@ -414,7 +516,7 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
          // leave this GPU, so that the NVLink rate of the fused kernel can be read next to its HBM rate
          static const char *names[3][3] = {{"", "p2p_x_y", ""}, {"p2p_y_x", "", "p2p_y_z"}, {"", "p2p_z_y", ""}};
          ProfScope ps(ctx, (!last && np > 1) ? names[pen][st[s + 1].pencil] : "p2p_none", remote_bytes);
-         run_stage(ctx, p.f64, mode, pen, dc, dr, cur, om, rptr, backward, passthrough, true);
+         run_chain_stage(p, s, mode, pen, dc, dr, cur, om, rptr, backward, passthrough);
       }
       if (last) break;
       const int nxt = st[s + 1].pencil;
@@ -449,13 +551,7 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
 static void ensure_work(Plan &p, bool c2c, bool at_plan_creation)
 {
    Ctx *ctx = p.ctx;
-   const size_t wb = uniform_work_bytes(p, c2c);
-   const int nbuf = ctx->nranks > 1 ? 3 : 2;
-   bool grow = false;
-   for (int i = 0; i < nbuf; i++) grow = grow || ctx->work_bytes[i] < wb;
-   if (!grow && !at_plan_creation) return;
-   for (int i = 0; i < nbuf; i++) ctx->reserve(i, wb);
-   p2p_publish(ctx); // collective (no-op for a single rank / in-process groups)
+   ctx->ensure_buffers(ctx->nranks > 1 ? kCtxBuffers : 2, uniform_work_bytes(p, c2c), at_plan_creation);
 }
 
 Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])
@@ -480,10 +576,13 @@ Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int i
 void plan_destroy(Plan *p)
 {
    if (!p) return;
-   cudaSetDevice(p->ctx->device);
-   cudaStreamSynchronize(p->ctx->stream);
-   if (p->stage_in) cudaFree(p->stage_in);
-   if (p->stage_out) cudaFree(p->stage_out);
+   try { p->ctx->sync_all(); } catch (...) {}
+   for (auto &io : p->io) {
+      if (io.in) cudaFree(io.in);
+      if (io.out) cudaFree(io.out);
+      if (io.in_done) cudaEventDestroy(io.in_done);
+      if (io.out_done) cudaEventDestroy(io.out_done);
+   }
    delete p;
 }
 
@@ -536,20 +635,24 @@ static void plan_bytes(const Plan *p, size_t b[4], int isign)
    b[3] = (size_t)2 * rs * p->ph.d.pencil_elems(xyz ? 2 : 0);
 }
 
-static void ensure_stage(Plan *p, size_t bi, size_t bo)
+static void ensure_stage(Plan *p, int which, size_t bi, size_t bo)
 {
-   if (bi > p->stage_in_bytes) {
-      if (p->stage_in) D2D_CHECK_CUDA(cudaFree(p->stage_in));
-      p->stage_in = nullptr; p->stage_in_bytes = 0;
-      D2D_CHECK_CUDA(cudaMalloc(&p->stage_in, bi));
-      p->stage_in_bytes = bi;
+   Plan::HostIo &io = p->io[which];
+   if (bi > io.in_bytes || bo > io.out_bytes) p->ctx->sync_all(); // nothing may still use the old staging arrays
+   if (bi > io.in_bytes) {
+      if (io.in) D2D_CHECK_CUDA(cudaFree(io.in));
+      io.in = nullptr; io.in_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&io.in, bi));
+      io.in_bytes = bi;
    }
-   if (bo > p->stage_out_bytes) {
-      if (p->stage_out) D2D_CHECK_CUDA(cudaFree(p->stage_out));
-      p->stage_out = nullptr; p->stage_out_bytes = 0;
-      D2D_CHECK_CUDA(cudaMalloc(&p->stage_out, bo));
-      p->stage_out_bytes = bo;
+   if (bo > io.out_bytes) {
+      if (io.out) D2D_CHECK_CUDA(cudaFree(io.out));
+      io.out = nullptr; io.out_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&io.out, bo));
+      io.out_bytes = bo;
    }
+   if (!io.in_done) D2D_CHECK_CUDA(cudaEventCreateWithFlags(&io.in_done, cudaEventDisableTiming));
+   if (!io.out_done) D2D_CHECK_CUDA(cudaEventCreateWithFlags(&io.out_done, cudaEventDisableTiming));
 }
 
 void plan_reserve_host_staging(Plan *p)
@@ -557,39 +660,128 @@ void plan_reserve_host_staging(Plan *p)
    size_t b[4];
    plan_bytes(p, b, D2D_FFT_FORWARD);
    D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
-   ensure_stage(p, std::max(b[0], std::max(b[1], b[2])), std::max(b[0], std::max(b[1], b[3])));
+   ensure_stage(p, 0, b[0], b[1]);
+   ensure_stage(p, 1, b[1], b[0]);
 }
+
+// decomp_2d_fft_3d on HOST arrays: upload, transform, download -- as three pipelines on three streams.
+//   * uploads (H2D) run on the context's upload stream in kHostPieces pieces, downloads (D2H) on its download stream, the
+//     transform on the context's stream; PCIe is full duplex, so the download of one call overlaps the upload of the next;
+//   * an x stage on the user's X-pencil starts on the z-slabs that have arrived and hands finished z-slabs to the download
+//     stream while it works on the next ones (IoGate);
+//   * host-memory dependencies between calls are tracked per piece: an upload from a host range that an earlier download
+//     is still writing waits only for the pieces it reads, so the spectrum of r2c_host can travel back up for c2r_host
+//     while its tail is still coming down.
+// With the context in blocking mode (default, like the reference) every call returns when its output is complete on the
+// host; with d2d_ctx_set_blocking(ctx, 0) calls return once enqueued and d2d_ctx_sync() completes them.
+constexpr int kHostPieces = 16;
 
 void fft_3d_host(Plan *p, int which /*0 r2c, 1 c2r, 2 c2c*/, const void *in_h, void *out_h, int isign)
 {
+   Ctx *ctx = p->ctx;
    size_t b[4];
    plan_bytes(p, b, isign);
    const size_t bi = which == 0 ? b[0] : which == 1 ? b[1] : b[2];
    const size_t bo = which == 0 ? b[1] : which == 1 ? b[0] : b[3];
-   D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
-   ensure_stage(p, bi, bo);
-   cudaStream_t st = p->ctx->stream;
+   D2D_CHECK_CUDA(cudaSetDevice(ctx->device));
+   ensure_stage(p, which, bi, bo);
+   Plan::HostIo &io = p->io[which];
+   for (int k = 0; k < 2; k++)
+      if (!ctx->io_stream[k]) D2D_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream[k], cudaStreamNonBlocking));
+   cudaStream_t up = ctx->io_stream[0], dn = ctx->io_stream[1], st = ctx->stream;
+   Ctx::HostTrack &ht = ctx->host;
+   auto overlaps = [](const char *a, size_t na, const char *b2, size_t nb) { return a < b2 + nb && b2 < a + na; };
+
+   // ---- upload ----------------------------------------------------------------------------------------------------
+   D2D_CHECK_CUDA(cudaStreamWaitEvent(up, io.in_done, 0)); // the previous transform of this kind has read its staging input
+   const char *hin = (const char *)in_h;
+   const bool raw = ht.d2h_base && overlaps(hin, bi, ht.d2h_base, ht.d2h_bytes);
+   std::vector<size_t> ucut(kHostPieces + 1);
+   for (int c = 0; c <= kHostPieces; c++) ucut[c] = c == kHostPieces ? bi : (bi / kHostPieces * c) / 4096 * 4096;
+   std::vector<cudaEvent_t> uev(kHostPieces);
    {
-      ProfScope ps(p->ctx, "h2d", (double)bi);
-      D2D_CHECK_CUDA(cudaMemcpyAsync(p->stage_in, in_h, bi, cudaMemcpyHostToDevice, st));
+      ProfScope ps(ctx, "h2d", (double)bi, up);
+      for (int c = 0; c < kHostPieces; c++) {
+         const size_t lo = ucut[c], hi = ucut[c + 1];
+         if (raw) { // wait for the download pieces that write [hin + lo, hin + hi): they are ordered, so the last one that overlaps
+            int lastp = -1;
+            for (size_t q = 0; q < ht.d2h_cut.size(); q++) {
+               const size_t plo = ht.d2h_cut[q].first, phi = ht.d2h_cut[q].second;
+               if (overlaps(hin + lo, hi - lo, ht.d2h_base + plo, phi - plo)) lastp = (int)q;
+            }
+            if (lastp >= 0) D2D_CHECK_CUDA(cudaStreamWaitEvent(up, ht.d2h_ev[lastp], 0));
+         }
+         if (hi > lo) D2D_CHECK_CUDA(cudaMemcpyAsync((char *)io.in + lo, hin + lo, hi - lo, cudaMemcpyHostToDevice, up));
+         uev[c] = ctx->new_sync_event();
+         D2D_CHECK_CUDA(cudaEventRecord(uev[c], up));
+      }
    }
-   if (which == 0) fft_3d_r2c(p, p->stage_in, p->stage_out);
-   else if (which == 1) {
-      const int keep = p->inplace;
-      p->inplace = 1; // the staging copy may be clobbered
-      fft_3d_c2r(p, p->stage_in, p->stage_out);
-      p->inplace = keep;
-   } else {
-      const int keep = p->inplace;
-      p->inplace = 1;
-      fft_3d_c2c(p, p->stage_in, p->stage_out, isign);
-      p->inplace = keep;
+   if (!ht.h2d_done) D2D_CHECK_CUDA(cudaEventCreateWithFlags(&ht.h2d_done, cudaEventDisableTiming));
+   D2D_CHECK_CUDA(cudaEventRecord(ht.h2d_done, up));
+   ht.h2d_base = hin;
+   ht.h2d_bytes = bi;
+
+   // ---- download side bookkeeping ----------------------------------------------------------------------------------
+   D2D_CHECK_CUDA(cudaStreamWaitEvent(st, io.out_done, 0)); // the previous download out of this staging output has finished
+   char *hout = (char *)out_h;
+   if (ht.h2d_base && overlaps(hout, bo, ht.h2d_base, ht.h2d_bytes)) D2D_CHECK_CUDA(cudaStreamWaitEvent(dn, ht.h2d_done, 0));
+   if (ht.d2h_base && overlaps(hout, bo, ht.d2h_base, ht.d2h_bytes) && !ht.d2h_cut.empty())
+      D2D_CHECK_CUDA(cudaStreamWaitEvent(dn, ht.d2h_ev[ht.d2h_cut.size() - 1], 0)); // write after write: keep the order
+   ht.d2h_base = hout;
+   ht.d2h_bytes = bo;
+   ht.d2h_cut.clear();
+   Ctx::Pending dspan{};
+   bool dspan_open = false;
+   auto download = [&](size_t lo, size_t hi) {
+      hi = std::min(hi, bo);
+      if (lo >= hi) return;
+      cudaEvent_t done = ctx->new_sync_event();
+      D2D_CHECK_CUDA(cudaEventRecord(done, st));
+      D2D_CHECK_CUDA(cudaStreamWaitEvent(dn, done, 0));
+      if (ctx->profiling && !dspan_open) { ctx->prof_begin("d2h", (double)bo, dspan, dn); dspan_open = true; }
+      D2D_CHECK_CUDA(cudaMemcpyAsync(hout + lo, (const char *)io.out + lo, hi - lo, cudaMemcpyDeviceToHost, dn));
+      const size_t q = ht.d2h_cut.size();
+      D2D_REQUIRE(q < Ctx::HostTrack::kMaxPieces, "too many download pieces");
+      if (!ht.d2h_ev[q]) D2D_CHECK_CUDA(cudaEventCreateWithFlags(&ht.d2h_ev[q], cudaEventDisableTiming));
+      D2D_CHECK_CUDA(cudaEventRecord(ht.d2h_ev[q], dn));
+      ht.d2h_cut.push_back({lo, hi});
+   };
+   IoGate gate;
+   gate.nio = kHostPieces;
+   gate.need_in = [&](size_t lo, size_t hi) {
+      hi = std::min(hi, bi);
+      int lastc = -1;
+      for (int c = 0; c < kHostPieces; c++)
+         if (ucut[c] < hi && lo < ucut[c + 1]) lastc = c;
+      if (lastc >= 0) D2D_CHECK_CUDA(cudaStreamWaitEvent(st, uev[lastc], 0)); // pieces are uploaded in order
+   };
+   gate.have_out = download;
+
+   // which pencils the user arrays are: the gates act slab-wise on X-pencils only
+   const bool fx = p->format == D2D_PHYSICAL_IN_X;
+   int pin, pout;
+   if (which == 0) { pin = fx ? 0 : 2; pout = fx ? 2 : 0; }
+   else if (which == 1) { pin = fx ? 2 : 0; pout = fx ? 0 : 2; }
+   else {
+      const bool xyz = (fx && isign == D2D_FFT_FORWARD) || (!fx && isign == D2D_FFT_BACKWARD);
+      pin = xyz ? 0 : 2; pout = xyz ? 2 : 0;
    }
-   {
-      ProfScope ps(p->ctx, "d2h", (double)bo);
-      D2D_CHECK_CUDA(cudaMemcpyAsync(out_h, p->stage_out, bo, cudaMemcpyDeviceToHost, st));
+   if (pin != 0) gate.need_in(0, bi); // the whole input first
+   p->gate = &gate;
+   try {
+      if (which == 0) fft_3d_r2c(p, io.in, io.out);
+      else if (which == 1) fft_3d_c2r(p, io.in, io.out);
+      else fft_3d_c2c(p, io.in, io.out, isign);
+   } catch (...) {
+      p->gate = nullptr;
+      throw;
    }
-   D2D_CHECK_CUDA(cudaStreamSynchronize(st)); // host results must be complete on return
+   p->gate = nullptr;
+   D2D_CHECK_CUDA(cudaEventRecord(io.in_done, st));
+   if (pout != 0 || ht.d2h_cut.empty()) download(0, bo); // not announced slab by slab: the whole output now
+   if (dspan_open) ctx->prof_end(dspan, dn);
+   D2D_CHECK_CUDA(cudaEventRecord(io.out_done, dn));
+   ctx->finish_call(); // blocking contexts: host results are complete on return
 }
 
 void plan_get_size(const Plan *p, int istart[3], int iend[3], int isize[3])

@@ -38,16 +38,20 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
    const int me = (from == 0 || to == 0) ? d.c1 : d.c2;
    void *nsrc = const_cast<void *>(src);
    CopyArgs c{};
+   // pack / receive buffers: the context's work buffers 0 and 1, sized for the largest pencil of ANY rank so that every rank
+   // grows (and republishes to its peers) at the same call -- a rank-local size would leave the peers with stale mappings
+   ctx->ensure_buffers(2, uniform_pencil_bytes(ctx, d, es), false);
+   void *w1 = ctx->work[0], *w2 = ctx->work[1];
+   const bool p2p = p2p_active(ctx);
    switch (direction) {
    case D2D_X_TO_Y:
    case D2D_Y_TO_X: {
-      void *w1 = ctx->reserve(0, (size_t)es * d.pencil_elems(from));
-      void *w2 = ctx->reserve(1, (size_t)es * d.pencil_elems(to));
+      ctx->wait_buffer_idle(0, ctx->stream);
       c.in = natural_map(d, from, nsrc);
       c.out = send_map(d, from, to, w1, es);
       pencil_space(d, from, c);
       launch_copy(ctx, c, es);
-      exchange(ctx, d, from, to, w1, w2, es);
+      exchange(ctx, d, from, to, w1, w2, es, 0, 1);
       c.in = recv_map(d, from, to, w2, w1, es);
       c.out = natural_map(d, to, dst);
       pencil_space(d, to, c);
@@ -55,18 +59,25 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
       break;
    }
    case D2D_Y_TO_Z: { // the receive buffer IS the Z pencil (transpose_y_to_z.f90:538)
-      void *w1 = ctx->reserve(0, (size_t)es * d.pencil_elems(1));
+      ctx->wait_buffer_idle(0, ctx->stream);
       c.in = natural_map(d, 1, nsrc);
       c.out = send_map(d, 1, 2, w1, es);
       c.out.ptr[me] = (char *)dst + (size_t)es * d.z2disp[me]; // own block goes straight home
       pencil_space(d, 1, c);
       launch_copy(ctx, c, es);
-      exchange(ctx, d, 1, 2, w1, dst, es);
+      if (!p2p) {
+         exchange(ctx, d, 1, 2, w1, dst, es, 0, -1);
+      } else { // peers push into the mapped work buffer; the blocks (contiguous z-slabs) then move home
+         exchange(ctx, d, 1, 2, w1, w2, es, 0, 1);
+         for (int m = 0; m < d.p_col; m++)
+            if (m != me && d.z2cnts[m])
+               D2D_CHECK_CUDA(cudaMemcpyAsync((char *)dst + (size_t)es * d.z2disp[m], (char *)w2 + (size_t)es * d.z2disp[m],
+                                              (size_t)es * d.z2cnts[m], cudaMemcpyDeviceToDevice, ctx->stream));
+      }
       break;
    }
    case D2D_Z_TO_Y: { // the send buffer IS the Z pencil (transpose_z_to_y.f90:418)
-      void *w2 = ctx->reserve(1, (size_t)es * d.pencil_elems(1));
-      exchange(ctx, d, 2, 1, src, w2, es);
+      exchange(ctx, d, 2, 1, src, w2, es, -1, 1);
       c.in = recv_map(d, 2, 1, w2, nsrc, es);
       c.out = natural_map(d, 1, dst);
       pencil_space(d, 1, c);

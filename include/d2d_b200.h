@@ -42,7 +42,7 @@ enum { D2D_PHYSICAL_IN_X = 1, D2D_PHYSICAL_IN_Z = 3 };
 enum { D2D_X_TO_Y = 0, D2D_Y_TO_Z = 1, D2D_Z_TO_Y = 2, D2D_Y_TO_X = 3 };
 enum { D2D_MEMCPY_H2D = 1, D2D_MEMCPY_D2H = 2, D2D_MEMCPY_D2D = 3 };
 /* transports of the all-to-all */
-enum { D2D_TRANSPORT_NONE = 0, D2D_TRANSPORT_NCCL = 1, D2D_TRANSPORT_LOCAL = 2 };
+enum { D2D_TRANSPORT_NONE = 0, D2D_TRANSPORT_NCCL = 1, D2D_TRANSPORT_LOCAL = 2, D2D_TRANSPORT_BOOT = 3 };
 
 /* ---- communicator / context --------------------------------------------------------------------
  * replaces decomp_2d_nccl_init/_fin (src/decomp_2d_nccl.f90:151-211) and the rank/coord bookkeeping
@@ -51,6 +51,13 @@ enum { D2D_TRANSPORT_NONE = 0, D2D_TRANSPORT_NCCL = 1, D2D_TRANSPORT_LOCAL = 2 }
  * sharing coord(1).  The unique id replaces the MPI_Bcast of ncclUniqueId (decomp_2d_nccl.f90:185). */
 int d2d_get_unique_id(unsigned char id[128]);
 int d2d_ctx_create(d2d_ctx **ctx, const unsigned char id[128], int nranks, int rank, int p_row, int p_col, int device);
+/* The same without NCCL: the caller supplies a blocking all-gather of `bytes` host bytes per rank over the ranks of the
+ * job (MPI_Allgather on decomp_2d_comm in the Fortran shim -- the reference bootstraps NCCL through MPI the same way,
+ * src/decomp_2d_nccl.f90:181-191; torch.distributed in the Python mirror).  It is used at context / plan creation only
+ * (exchange of CUDA-IPC handles); the data plane is the library's own peer-memory exchange (copy engines and peer stores
+ * over NVLink with stream-ordered flags).  Returns non-zero from the callback to report failure. */
+typedef int (*d2d_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes);
+int d2d_ctx_create_bootstrap(d2d_ctx **ctx, int nranks, int rank, int p_row, int p_col, int device, d2d_allgather_fn allgather, void *user);
 /* thread-per-rank mode inside one process (any number of ranks per device): the exchange is a
  * device-to-device copy between the rank buffers.  Used where NCCL cannot run (several ranks on one
  * GPU) and for single-process multi-GPU drivers. */

@@ -131,6 +131,17 @@ void orc_decomp_init(int nx, int ny, int nz, int p_row, int p_col, int rank, orc
 
 int orc_sizeof_decomp(void) { return (int)sizeof(orc_decomp); }
 
+/* One OpenMP thread plays one MPI rank of the simulated world.  Launchers such as torchrun export OMP_NUM_THREADS=1,
+ * which would silently serialise the ranks: the harness sets the thread count explicitly and reads it back. */
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_get_max_threads(void) { return 1; }
+#endif
+
 /* best_2d_grid  (src/decomp_2d_init_fin.f90:270-300) with findfactor (src/factor.f90).
  * The reference lists the factors of nproc in increasing order (<= sqrt, then their complements)
  * and picks col = factors(nfact/2+1), row = nproc/col. */

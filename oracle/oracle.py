@@ -72,6 +72,12 @@ class Decomp:
         return (self.xst, self.yst, self.zst)[pencil]
 
 
+def set_threads(n):
+    """OpenMP threads of the rank loops (one thread plays one MPI rank); returns the count now in effect."""
+    lib().orc_set_threads(int(n))
+    return int(lib().orc_get_max_threads())
+
+
 def best_2d_grid(nproc):
     r, c = C.c_int(), C.c_int()
     lib().orc_best_2d_grid(nproc, C.byref(r), C.byref(c))

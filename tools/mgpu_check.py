@@ -18,16 +18,27 @@ from __graft_entry__ import package
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # MGPU_BACKEND=gloo: torch.distributed only carries the bootstrap all-gather (transport "boot": no NCCL anywhere), which
+    # also lets several ranks share one GPU -- the peer-memory exchange (CUDA IPC + copy engines + stream-ordered flags) is the
+    # same code whether the peer's buffer lives on another GPU or on this one
+    backend = os.environ.get("MGPU_BACKEND", "nccl")
+    dev = local % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo")
     p = package()
     grids = {1: [(1, 1)], 2: [(1, 2), (2, 1)], 4: [(2, 2), (1, 4), (4, 1)], 8: [(2, 4), (4, 2)]}[world]
     if len(sys.argv) > 2:
         grids = [(int(sys.argv[1]), int(sys.argv[2]))]
+    shapes = ((32, 16, 64), (256, 64, 512), (64, 256, 32))
+    if os.environ.get("MGPU_SHAPES") == "small":
+        shapes = ((32, 16, 64), (64, 256, 32))
     worst = 0.0
     nfail = 0
     for grid in grids:
-        for shape in ((32, 16, 64), (256, 64, 512), (64, 256, 32)):
+        for shape in shapes:
             for fmt in (p.PHYSICAL_IN_Z, p.PHYSICAL_IN_X):
                 if fmt == p.PHYSICAL_IN_X and shape[0] % 2:
                     continue
@@ -81,7 +92,7 @@ def main():
                     print(f"rank {rank} grid {grid} shape {shape} fmt {fmt}: r2c {e1:.2e} c2r {e2:.2e} c2c {e3:.2e} transposes "
                           f"{'exact' if t_ok else 'WRONG'} {'FAIL' if bad else 'ok'}", flush=True)
                 p.decomp_2d_finalize()
-    t = torch.tensor([nfail], device="cuda")
+    t = torch.tensor([nfail], device="cuda" if backend == "nccl" else "cpu")
     dist.all_reduce(t)
     if rank == 0:
         print(f"mgpu_check: world {world}, failures {int(t.item())}, worst rel err {worst:.2e}", flush=True)
