@@ -67,6 +67,10 @@ struct FftArgs2 {
    // spectral pencils of PHYSICAL_IN_X): first column of tile ta of row b is ta * W - ((shift0 + b * shift_b) mod W),
    // W = lines per landing row; columns < 0 do not exist.  tiles_a counts the (possibly one more) tiles per b.
    int shift_on, shift0, shift_b, tiles_a;
+   // merged landing only: the boxes land with the TMA engine's 128-byte swizzle (16-byte chunk index of a row XOR row mod 8)
+   // and the two sub-tiles own the chunks of even / odd index instead of the first / second half of a row: the 8 lanes of a
+   // quarter warp (4 chunks of row r, 4 of row r + 1) then read 8 distinct 16-byte bank groups instead of the same 4 twice
+   int swz;
    LoadOp ops[kMaxLoadOps];
 };
 
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    static_assert(MODE == MODE_C2C || INL == IN_TILE || TX % 2 == 0, "real line pairs must land in the same zone");
    constexpr int SP = TX;
    constexpr int N = P::N, E = P::E, TPL = P::T, NH = N / 2 + 1;
-   extern __shared__ __align__(128) unsigned char smem2_raw[];
+   extern __shared__ __align__(1024) unsigned char smem2_raw[];
    unsigned char *smem_raw = smem2_raw;
    const FftArgs &g = g2.a;
 
@@ -294,9 +298,16 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
    const int ngroups = MRG ? groups_a * g.nb : (ntiles + LY - 1) / LY;
    T2 *lsm = reinterpret_cast<T2 *>(Xbase + (size_t)ly * G::x_sub) + tx;
    // landing zones as this thread reads them: row r of the early zone at Lmine + r * land_row_bytes (MRG: the zones are
-   // shared, the sub-tile owns row_bytes at offset ly * row_bytes of every row)
-   const unsigned char *Lmine = MRG ? Lbase + (size_t)ly * G::row_bytes : Lbase + (size_t)ly * G::l_sub;
-   const unsigned char *Xmine = MRG ? Xbase + (size_t)ly * G::row_bytes : Xbase + (size_t)ly * G::x_sub + G::late_skew;
+   // shared, the sub-tile owns row_bytes at offset ly * row_bytes of every row -- or, swizzled, every other 16-byte chunk)
+   // mrg_c: index of this thread's line among the LY * TX lines of the group; mrg_off: its byte offset inside a landing row
+   constexpr int EPC = 16 / (int)sizeof(T2); // lines per 16-byte chunk of a landing row (C2C / R2C)
+   const bool swz = MRG && g2.swz != 0;
+   const int mrg_c = swz ? ((tx / EPC) * LY + ly) * EPC + tx % EPC : ly * TX + tx;
+   const int mrg_off = swz ? ((((tx / EPC) * LY + ly) ^ (j & 7)) << 4) + (tx % EPC) * (int)sizeof(T2) : mrg_c * (int)sizeof(T2);
+   static_assert(!MRG || (TPL % 8 == 0 && G::rows_early % 8 == 0), "swizzled landing: the row phase must be the thread's j mod 8");
+   const unsigned char *Lmine = MRG ? Lbase + mrg_off : Lbase + (size_t)ly * G::l_sub;
+   const unsigned char *Xmine = MRG ? Xbase + mrg_off : Xbase + (size_t)ly * G::x_sub + G::late_skew;
+   const int tile_idx = MRG ? 0 : tx; // element of a landing row (C2C / R2C tiles): MRG rows are addressed through mrg_off
 
    {
       const T2 *__restrict__ twg = reinterpret_cast<const T2 *>(g.tw);
@@ -421,9 +432,9 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
       bool in_range;
       if constexpr (MRG) {
          b = grp / groups_a;
-         const int ta = (grp - b * groups_a) * LY + ly;
+         const int ta = (grp - b * groups_a) * LY + (swz ? 0 : ly);
          in_range = ta < tiles_a;
-         a = ta * TX + tx - col_shift(b);
+         a = (grp - b * groups_a) * (LY * TX) + mrg_c - col_shift(b);
       } else {
          const int tile = grp * LY + ly;
          in_range = tile < ntiles;
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             T2 x;
             if constexpr (INL == IN_TILE) {
                const unsigned char *src = (row < G::rows_early) ? Lmine + (size_t)row * G::land_row_bytes : Xmine + (size_t)(row - G::rows_early) * G::land_row_bytes;
-               x = reinterpret_cast<const T2 *>(src)[tx];
+               x = reinterpret_cast<const T2 *>(src)[tile_idx];
             } else if constexpr (MODE == MODE_C2C) {
                const unsigned char *line = (tx < G::lines_early) ? Lmine + (size_t)tx * G::line_pitch : Xmine + (size_t)(tx - G::lines_early) * G::line_pitch;
                x = reinterpret_cast<const T2 *>(line)[row];

@@ -220,9 +220,18 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
    // Always K chunks (empty ones allowed): every rank of the grid then issues the same number of exchanges whatever its
    // own extents are, which the in-process transport (one barrier over all ranks per exchange) and the chunk sequence
    // numbers of the peer-memory path rely on.
+   // The first and the last chunk are half as long as the others: the exchange cannot start before the first chunk is
+   // written and the consumer's last chunk cannot start before the last one has landed, so those two set the part of a link
+   // that nothing overlaps (measured on 2 B200s, 1024^3: 10.9 ms per pair with equal chunks).
+   static const double edge = getenv("D2D_CHUNK_EDGE") ? atof(getenv("D2D_CHUNK_EDGE")) : 0.5;
    auto bounds = [&](int nf) {
       std::vector<int> b(K + 1, 0);
-      for (int c = 1; c < K; c++) b[c] = std::max(b[c - 1], (int)((long long)nf * c / K) / 16 * 16);
+      const double total = K <= 2 ? (double)K : (K - 2) + 2 * edge;
+      double acc = 0;
+      for (int c = 1; c < K; c++) {
+         acc += (K <= 2 || (c > 1)) ? 1.0 : edge; // weight of chunk c - 1
+         b[c] = std::max(b[c - 1], (int)((double)nf * acc / total) / 16 * 16);
+      }
       b[K] = nf;
       return b;
    };

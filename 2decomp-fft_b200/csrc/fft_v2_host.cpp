@@ -52,6 +52,7 @@ struct Builder {
    int nmaps = 0;
    struct Key { int piece, box_rows; } keys[kMaxTmaps];
    int swap[kMaxTmaps];
+   bool swizzle = false; // 128-byte swizzle of the landing rows (merged landing, fft_kernel_v2.cuh FftArgs2::swz)
    int find_or_make(int piece, int box_rows, const PieceDesc &d, int f64, int box0)
    {
       for (int i = 0; i < nmaps; i++)
@@ -80,7 +81,8 @@ struct Builder {
                                         : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                      : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
       CUresult r = fn(&tm.m[nmaps], es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.base, dims, strides, box,
-                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return -1;
       keys[nmaps] = {piece, box_rows};
       swap[nmaps] = sw ? 1 : 0;
@@ -183,6 +185,22 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       a2.c0_mul = k->row_bytes / es / k->tx; // scalars per line along dim 0
       int row = 0; // global row (along e) of the tile
       a2.nops = 0;
+      // swizzled landing (merged kernels, 128-byte rows): every box must start on a multiple of 8 rows, so that the swizzle
+      // phase of a row is its index mod 8 whatever the engine derives it from (box row or shared-memory address bits)
+      static const int swz_enabled = env_int("D2D_V2_SWIZZLE", 1);
+      if (swz_enabled && k->merged && land_row_bytes == 128 && k->rows_early % 8 == 0) {
+         bool ok = true;
+         for (int m = 0; m < np && mode != MODE_R2C; m++) {
+            const int len = g.in.e0[m + 1] - g.in.e0[m];
+            ok = ok && (g.in.e0[m] % 8 == 0) && (len % 8 == 0 || m == np - 1);
+         }
+         if (mode == MODE_R2C) ok = (N % 8 == 0);
+         // tail boxes shorter than 8 rows may only come last: a piece of length 8 q + r (r < 8) is cut 256, ..., 8, then 4 / 2 / 1
+         const int last_len = (mode == MODE_R2C) ? N : g.in.e0[np] - g.in.e0[np - 1];
+         const int tail = last_len % 8;
+         ok = ok && (tail == 0 || tail == 1 || tail == 2 || tail == 4); // at most one box below 8 rows
+         B.swizzle = ok;
+      }
       for (int m = 0; m < np; m++) {
          PieceDesc d{};
          int len;
@@ -229,6 +247,7 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       }
       if (row != rows_total) return false;
    }
+   a2.swz = B.swizzle ? 1 : 0;
    // ---- column shift (C2C): make the rows of the tile side start on full-row boundaries -------------------------
    a2.tiles_a = (g.na + k->tx - 1) / k->tx;
    static const int shift_enabled = env_int("D2D_V2_SHIFT", 1);
@@ -238,7 +257,7 @@ bool fft_v2_try_launch(Ctx *ctx, const FftArgs &g, int f64, int mode, cudaError_
       long long se = 0, sb = 0;
       // tile INPUTS: measured no gain (TMA boxes are insensitive to the row phase: c2c_z_bwd 3.97 vs 4.10 ms), so only
       // D2D_V2_SHIFT=2 shifts them; tile OUTPUTS (LSU stores) gain 5.35 -> 3.34 ms (profiles/r01_h_kernels_ab.txt)
-      if (inl == IN_TILE && g.in.np == 1 && shift_enabled >= 2) { ptr = g.in.ptr[0]; se = g.in.se[0]; sb = g.in.sb[0]; }
+      if (inl == IN_TILE && g.in.np == 1 && shift_enabled >= 2 && !B.swizzle) { ptr = g.in.ptr[0]; se = g.in.se[0]; sb = g.in.sb[0]; }
       else if (inl == IN_LINE && tile_out && g.out.np == 1) { ptr = g.out.ptr[0]; se = g.out.se[0]; sb = g.out.sb[0]; }
       if (ptr && ((uintptr_t)ptr % ces) == 0 && (se % W) == 0 && se > 0 && sb >= 0) {
          const int off0 = (int)(((uintptr_t)ptr / ces) % W), offb = (int)(sb % W);

@@ -446,6 +446,8 @@ def main():
 
         e2e_step()  # warm-up (allocates the device staging buffers)
         d2d.sync()
+        d2d.profile_reset()
+        d2d.profile(True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -453,6 +455,10 @@ def main():
         d2d.sync()  # every stream of the context: the last download is on the host
         wall_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
         barrier()
+        d2d.profile(False)
+        eprof = d2d.profile_read()
+        pcie = {k: {"ms_per_call": round(eprof[k][0] / eprof[k][1], 2), "GBps": round(eprof[k][2] / eprof[k][0] / 1e6, 1)}
+                for k in ("h2d", "d2h") if k in eprof and eprof[k][1] and eprof[k][0] > 0}
         ems = allmax(wall_ms)
         m = min(h_in.numel(), 1 << 24)  # a sample is enough for a guard (the full check ran on the device above)
         rt2 = float((h_back[:m] / float(n) ** 3 - h_in[:m]).abs().max().item())
@@ -464,7 +470,7 @@ def main():
                "api": "d2d_fft_3d_r2c_host + d2d_fft_3d_c2r_host (pinned host arrays; context in stream-ordered mode, "
                       "d2d_ctx_sync at the end of the timed loop)",
                "steps": args.e2e_steps, "timing": "wall clock between device-synchronised points, max over ranks",
-               "round_trip_max_err": max(rt2, rt3)}
+               "round_trip_max_err": max(rt2, rt3), "pcie_spans": pcie}
         del h_in, h_spec, h_back
 
     cpu = None
