@@ -111,15 +111,19 @@ struct Ctx {
    // chunk-wise pipelined chains (fft_plan.cpp run_chain_pipe): the exchanges run on their own streams -- one per peer
    // of a communicator for the copy-engine pushes of the peer-memory path, comm_stream for the transports' exchanges
    cudaStream_t comm_stream = nullptr;
-   cudaStream_t copy_stream[kMaxP] = {};
+   cudaStream_t copy_stream[2 * kMaxP] = {};
    cudaStream_t io_stream[2] = {}; // host-array entry points: [0] uploads (H2D), [1] downloads (D2H)
    std::vector<cudaEvent_t> sync_events; // untimed events ordering the streams, reused between calls
    size_t next_sync_event = 0;
    std::vector<cudaEvent_t> buf_busy[kCtxBuffers]; // copies still reading work[w] (recorded on the copy streams)
+   cudaStream_t push_stream = nullptr; // the exchange kernels of the pipelined chains (highest priority)
+   int fft_grid_limit = 0;             // SMs the FFT kernels may occupy while exchange kernels share the device (0 = all)
    cudaStream_t copy_stream_for(int k);
    cudaEvent_t new_sync_event();
    void wait_buffer_idle(int w, cudaStream_t st); // st waits for the copies that read work[w]
-   void mark_buffer_busy(int w, int nstreams);    // record the current tail of copy streams 0..nstreams-1 against work[w]
+   void mark_buffer_busy(int w, int nstreams);
+   void mark_buffer_busy_on(int w, cudaStream_t st); // ... the current tail of `st`
+   int sm_count = 0;    // record the current tail of copy streams 0..nstreams-1 against work[w]
    // profiling
    bool profiling = false;
    std::vector<ProfEntry> prof;
@@ -183,6 +187,21 @@ struct CopyArgs {
 };
 void launch_copy(Ctx *ctx, const CopyArgs &c, int es);
 
+// ---- exchange kernel of the pipelined chains (push_kernels.cu) -------------------------------------------------------
+constexpr int kMaxPushSegs = 8;
+struct PushSeg {
+   const char *src; // this rank's send buffer
+   char *dst;       // the peer's receive buffer (CUDA-IPC mapped)
+   size_t bytes;
+};
+struct PushArgs {
+   int nseg, nflag;
+   PushSeg seg[kMaxPushSegs];
+   uint32_t *flag[kMaxPushSegs]; // arrival counters in the peers' memory: every CTA adds 1 when its stores are complete
+};
+int push_ctas(); // CTAs of a push launch (D2D_PUSH_CTAS): what one arrival is worth on the peers' counters
+void launch_push(const PushArgs &a, cudaStream_t st);
+
 // ---- twiddles -----------------------------------------------------------------------------------
 const void *twiddles_for(int device, int n, int f64, int compact = 0);
 void twiddles_release_all();
@@ -234,6 +253,10 @@ void *p2p_peer_work(const Ctx *ctx, int w, int rank);
 size_t p2p_peer_bytes(const Ctx *ctx, int w, int rank);
 uint32_t p2p_next_epoch(Ctx *ctx);
 uint32_t p2p_reserve_seq(Ctx *ctx, uint32_t n); // n consecutive chunk sequence numbers; returns the number before the first
+// per-peer arrival counters of the kernel-driven exchange (flags `which` = 3): the sender's kernels add push_ctas() per chunk,
+// the receiver waits for push_ctas() x (chunks expected from that peer so far)
+uint32_t p2p_expect_push(Ctx *ctx, int peer); // one more chunk expected from `peer`; returns the counter value to wait for
+uint32_t *p2p_push_flag(Ctx *ctx, int peer);  // address of this rank's arrival counter in `peer`'s memory
 // flags `which`: 0 ready (epochs), 1 done (epochs of the fused chain), 2 arrived (chunk sequence numbers of the pipelined chain)
 void p2p_signal(Ctx *ctx, int peer, int which, uint32_t value, cudaStream_t st = nullptr);
 void p2p_wait(Ctx *ctx, int peer, int which, uint32_t value, cudaStream_t st = nullptr);

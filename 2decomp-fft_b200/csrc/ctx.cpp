@@ -116,15 +116,16 @@ void Ctx::sync_all()
    D2D_CHECK_CUDA(cudaSetDevice(device));
    D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
    if (comm_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(comm_stream));
-   for (int k = 0; k < kMaxP; k++)
+   for (int k = 0; k < 2 * kMaxP; k++)
       if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
    for (cudaStream_t s : io_stream)
       if (s) D2D_CHECK_CUDA(cudaStreamSynchronize(s));
+   if (push_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(push_stream));
 }
 
 cudaStream_t Ctx::copy_stream_for(int k)
 {
-   D2D_REQUIRE(k >= 0 && k < kMaxP, "copy stream index out of range");
+   D2D_REQUIRE(k >= 0 && k < 2 * kMaxP, "copy stream index out of range");
    if (!copy_stream[k]) D2D_CHECK_CUDA(cudaStreamCreateWithFlags(&copy_stream[k], cudaStreamNonBlocking));
    return copy_stream[k];
 }
@@ -164,13 +165,23 @@ void Ctx::ensure_buffers(int nbuf, size_t bytes, bool force_publish)
    if (!grow && !force_publish && published) return;
    if (grow) {
       // nobody may still be copying out of / into the old buffers
-      for (int k = 0; k < kMaxP; k++)
+      for (int k = 0; k < 2 * kMaxP; k++)
          if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
       p2p_unpublish(this); // collective: every rank closes its mappings of the peers' buffers before anybody frees one
       for (int i = 0; i < nbuf; i++) reserve(i, bytes);
    }
    p2p_publish(this); // collective (no-op for a single rank / in-process groups)
    published = true;
+}
+
+void Ctx::mark_buffer_busy_on(int w, cudaStream_t st)
+{
+   if (buf_busy[w].empty()) {
+      cudaEvent_t e;
+      D2D_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      buf_busy[w].push_back(e);
+   }
+   D2D_CHECK_CUDA(cudaEventRecord(buf_busy[w][0], st));
 }
 
 void Ctx::prof_begin(const char *label, double bytes, Pending &p, cudaStream_t st)
@@ -204,7 +215,8 @@ void Ctx::prof_flush()
    if (pending.empty()) return;
    D2D_CHECK_CUDA(cudaStreamSynchronize(stream));
    if (comm_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(comm_stream));
-   for (int k = 0; k < kMaxP; k++)
+   if (push_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(push_stream));
+   for (int k = 0; k < 2 * kMaxP; k++)
       if (copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(copy_stream[k]));
    for (auto &p : pending) {
       float ms = 0;
@@ -225,10 +237,11 @@ Ctx::~Ctx()
    p2p = nullptr;
    tr.reset();
    if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
-   for (int k = 0; k < kMaxP; k++)
+   for (int k = 0; k < 2 * kMaxP; k++)
       if (copy_stream[k]) { cudaStreamSynchronize(copy_stream[k]); cudaStreamDestroy(copy_stream[k]); }
    for (cudaStream_t s : io_stream)
       if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+   if (push_stream) { cudaStreamSynchronize(push_stream); cudaStreamDestroy(push_stream); }
    for (auto e : host.d2h_ev)
       if (e) cudaEventDestroy(e);
    if (host.h2d_done) cudaEventDestroy(host.h2d_done);

@@ -50,6 +50,7 @@ template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
       int dev = 0;
       if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
       if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+      static int per_sm_of[kMaxDevices] = {0};
       int &resident = resident_of[dev];
       if (!resident) {
          if (smem > 48 * 1024) {
@@ -61,12 +62,14 @@ template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
          if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
          if (e != cudaSuccess) return e;
          if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+         per_sm_of[dev] = per_sm;
          resident = sms * per_sm;
       }
       const long long tiles = (long long)((g.na + TX - 1) / TX) * g.nb;
       const long long groups = (tiles + LY - 1) / LY;
       if (groups <= 0) return cudaSuccess;
-      const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
+      const long long cap = (g.sm_limit > 0 && g.sm_limit * per_sm_of[dev] < resident) ? g.sm_limit * per_sm_of[dev] : resident;
+      const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
       kern<<<blocks, G::threads, smem, st>>>(g);
       return cudaGetLastError();
    }
@@ -107,6 +110,7 @@ template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
       int dev = 0;
       if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
       if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+      static int per_sm_of[kMaxDevices] = {0};
       int &resident = resident_of[dev];
       if (!resident) {
          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -116,12 +120,14 @@ template <int MODE, int INL, int TX2, bool MRG = false> struct Inst2 {
          if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::threads, smem);
          if (e != cudaSuccess) return e;
          if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+         per_sm_of[dev] = per_sm;
          resident = sms * per_sm;
       }
       const long long tiles_a = g.tiles_a;
       const long long groups = MRG ? ((tiles_a + LY2 - 1) / LY2) * g.a.nb : (tiles_a * g.a.nb + LY2 - 1) / LY2;
       if (groups <= 0) return cudaSuccess;
-      const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
+      const long long cap = (g.a.sm_limit > 0 && g.a.sm_limit * per_sm_of[dev] < resident) ? g.a.sm_limit * per_sm_of[dev] : resident;
+      const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
       kern<<<blocks, G::threads, smem, st>>>(g, tm);
       return cudaGetLastError();
    }

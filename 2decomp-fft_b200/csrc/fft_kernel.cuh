@@ -57,6 +57,7 @@ struct FftArgs {
    int passthrough;    // 1: opt_skip_XYZ_c2c -- move data through the maps without transforming
    int debug;          // experiments only (D2D_DEBUG_SKIP): bit 0 = drop the global stores, bit 1 = drop the global loads
    const void *tw;     // twiddle tables of this n / dtype
+   int sm_limit;       // host side only: SMs the launch may occupy (0 = all): exchange kernels share the device
 };
 
 template <typename T> struct Vec2;

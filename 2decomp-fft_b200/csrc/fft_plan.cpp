@@ -66,6 +66,7 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    g.passthrough = passthrough;
    static const int dbg = getenv("D2D_DEBUG_SKIP") ? atoi(getenv("D2D_DEBUG_SKIP")) : 0;
    g.debug = dbg;
+   g.sm_limit = ctx->fft_grid_limit;
    int kind;
    if (chain) {
       fft_stage_batch(dc, pencil, g.na, g.nb);
@@ -214,16 +215,34 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
    const int padq = 128 / es;
    const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
    const bool ce = p2p_active(ctx);
+   // peer-memory plane: the chunks are pushed by the copy engines (default: one cudaMemcpyAsync per peer and chunk, 780 GB/s
+   // for large copies) or by the exchange kernel (D2D_PUSH=sm, push_kernels.cu: one launch per chunk for all peers; SM-issued
+   // writes reach 715 GB/s on NVLink and one driving thread per CTA sustains ~45 GB/s, so it needs 16+ SMs)
+   static const bool push_sm = getenv("D2D_PUSH") && std::string(getenv("D2D_PUSH")) == "sm";
+   const bool sm = ce && push_sm;
    if (!ce && !ctx->comm_stream) D2D_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+   struct LimitGuard { // the FFT kernels leave push_ctas() SMs to the exchange kernels for the duration of the chain
+      Ctx *c;
+      ~LimitGuard() { c->fft_grid_limit = 0; }
+   } limit_guard{ctx};
+   if (sm) {
+      if (!ctx->push_stream) {
+         int lo = 0, hi = 0;
+         D2D_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+         D2D_CHECK_CUDA(cudaStreamCreateWithPriority(&ctx->push_stream, cudaStreamNonBlocking, hi));
+         D2D_CHECK_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+      }
+      ctx->fft_grid_limit = std::max(1, ctx->sm_count - push_ctas());
+   }
    const bool real_link[2] = {comm_size(dc, st[0].pencil, st[1].pencil) > 1, comm_size(dc, st[1].pencil, st[2].pencil) > 1};
    // chunk boundaries of a link: K pieces of the free axis, cut on multiples of 16 lines (tiles and real pairs stay whole)
    // Always K chunks (empty ones allowed): every rank of the grid then issues the same number of exchanges whatever its
    // own extents are, which the in-process transport (one barrier over all ranks per exchange) and the chunk sequence
    // numbers of the peer-memory path rely on.
-   // The first and the last chunk are half as long as the others: the exchange cannot start before the first chunk is
-   // written and the consumer's last chunk cannot start before the last one has landed, so those two set the part of a link
-   // that nothing overlaps (measured on 2 B200s, 1024^3: 10.9 ms per pair with equal chunks).
-   static const double edge = getenv("D2D_CHUNK_EDGE") ? atof(getenv("D2D_CHUNK_EDGE")) : 0.5;
+   // D2D_CHUNK_EDGE < 1 makes the first and the last chunk shorter than the others (the exchange cannot start before the first
+   // chunk is written, the consumer's last chunk cannot start before the last one has landed); measured on 2 B200s at 1024^3 it
+   // changes nothing (10.9-11.1 ms per pair for 0.3 / 0.5 / 1.0): the chain is bound by HBM traffic there, not by those edges.
+   static const double edge = getenv("D2D_CHUNK_EDGE") ? atof(getenv("D2D_CHUNK_EDGE")) : 1.0;
    auto bounds = [&](int nf) {
       std::vector<int> b(K + 1, 0);
       const double total = K <= 2 ? (double)K : (K - 2) + 2 * edge;
@@ -236,18 +255,34 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
       return b;
    };
    for (int w = 0; w < kCtxBuffers; w++) D2D_REQUIRE(ctx->work_bytes[w] >= wbytes, "pipelined chain: work buffers were not reserved");
+   // "ready" for every link of the chain right away: the receive buffers 1 and 3 were last read by the previous chain, which
+   // precedes this point in stream order, so the peers never have to wait for this rank to REACH a link before they push
+   uint32_t link_epoch[2] = {0, 0};
+   if (ce)
+      for (int s = 0; s < 2; s++) {
+         if (!real_link[s]) continue;
+         link_epoch[s] = p2p_next_epoch(ctx);
+         const bool col = (st[s].pencil == 0 || st[s + 1].pencil == 0);
+         const int np = col ? ctx->p_row : ctx->p_col, me = col ? ctx->c1 : ctx->c2;
+         for (int k = 1; k < np; k++) {
+            const int m = (me + k) % np;
+            p2p_signal(ctx, col ? ctx->peer_rank_col(m) : ctx->peer_rank_row(m), 0, link_epoch[s]);
+         }
+      }
    PieceMap cur = fft_user_map(dc, st[0].pencil, in);
    // the link feeding the current stage
    struct Feed {
       bool chunked = false;
       std::vector<int> bounds;
       std::vector<cudaEvent_t> arrived; // transport plane: the exchange of chunk c has completed
-      uint32_t seq_base = 0;            // peer-memory plane: chunk c has landed when arrived_from[peer] >= seq_base + c + 1
+      uint32_t seq_base = 0;            // copy engines: chunk c has landed when arrived_from[peer] >= seq_base + c + 1
+      std::vector<std::vector<uint32_t>> pushed; // exchange kernel: ... when pushed_from[peers[i]] >= pushed[c][i]
       std::vector<int> peers;           // global ranks of the peers of the link
    } feed;
    auto wait_chunk = [&](int c) {
       ProfScope ps(ctx, "pipe_wait");
-      if (ce) for (int r : feed.peers) p2p_wait(ctx, r, 2, feed.seq_base + (uint32_t)c + 1);
+      if (sm) for (size_t i = 0; i < feed.peers.size(); i++) p2p_wait(ctx, feed.peers[i], 3, feed.pushed[c][i]);
+      else if (ce) for (int r : feed.peers) p2p_wait(ctx, r, 2, feed.seq_base + (uint32_t)c + 1);
       else D2D_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, feed.arrived[c], 0));
    };
    for (int s = 0; s < 3; s++) {
@@ -292,10 +327,18 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
          uint32_t epoch = 0;
          static const char *names[3][3] = {{"", "ce_x_y", ""}, {"ce_y_x", "", "ce_y_z"}, {"", "ce_z_y", ""}};
          std::vector<Ctx::Pending> spans(np);
+         static const int lanes_env = getenv("D2D_COPY_LANES") ? atoi(getenv("D2D_COPY_LANES")) : 1;
+         const int lanes = std::max(1, std::min(lanes_env, 2));
+         std::vector<cudaEvent_t> ready_seen(np), flagged(np);
          if (ce) {
-            epoch = p2p_next_epoch(ctx);
-            nf.seq_base = p2p_reserve_seq(ctx, (uint32_t)K);
-            for (int r : nf.peers) p2p_signal(ctx, r, 0, epoch); // stream order: this rank is done with the old contents of work[recv_w]
+            epoch = link_epoch[s];
+            if (sm) {
+               nf.pushed.resize(K);
+               for (int c = 0; c < K; c++)
+                  for (int r : nf.peers) nf.pushed[c].push_back(p2p_expect_push(ctx, r));
+            } else {
+               nf.seq_base = p2p_reserve_seq(ctx, (uint32_t)K);
+            }
          }
          for (int c = 0; c < K; c++) {
             StageRange rg;
@@ -305,11 +348,40 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
             D2D_CHECK_CUDA(cudaEventRecord(written, ctx->stream));
             LinkChunk S;
             fft_link_chunk(dc, pen, nxt, padq, b[c], b[c + 1], S);
-            if (ce) {
+            if (sm) {
+               cudaStream_t ps = ctx->push_stream;
+               D2D_CHECK_CUDA(cudaStreamWaitEvent(ps, written, 0));
+               if (c == 0) {
+                  for (int r : nf.peers) p2p_wait(ctx, r, 0, epoch, ps);
+                  if (ctx->profiling) ctx->prof_begin(names[pen][nxt], 0, spans[0], ps);
+               }
+               PushArgs pa{};
+               D2D_REQUIRE(np - 1 <= kMaxPushSegs, "too many peers for one exchange kernel");
                for (int k = 1; k < np; k++) {
                   const int m = (me + k) % np;
                   const int prank = nf.peers[k - 1];
-                  cudaStream_t cs = ctx->copy_stream_for(k - 1);
+                  LinkChunk R; // the consumer side ON THE DESTINATION rank: where it expects this rank's block
+                  fft_link_chunk(dpeer[m], nxt, pen, padq, b[c], b[c + 1], R);
+                  D2D_REQUIRE(R.cnt[me] == S.cnt[m], "pipelined chain: chunk sizes of the two sides disagree");
+                  char *dst = (char *)p2p_peer_work(ctx, recv_w, prank);
+                  const size_t off = (size_t)es * R.off[me], nbytes = (size_t)es * S.cnt[m];
+                  D2D_REQUIRE(dst != nullptr && off + nbytes <= p2p_peer_bytes(ctx, recv_w, prank), "pipelined chain: destination buffer too small");
+                  pa.flag[pa.nflag++] = p2p_push_flag(ctx, prank);
+                  if (nbytes) pa.seg[pa.nseg++] = PushSeg{(const char *)sendbuf + (size_t)es * S.off[m], dst + off, nbytes};
+                  if (ctx->profiling) ctx->prof[spans[0].idx].bytes += (double)nbytes;
+               }
+               launch_push(pa, ps);
+               ctx->launches++;
+               if (ctx->profiling && c == K - 1) ctx->prof_end(spans[0], ps);
+            } else if (ce) {
+               // copy engines: one cudaMemcpyAsync per peer and chunk.  A peer copy costs 25-40 us of dead time on its
+               // stream (launch, completion flush, flag), so consecutive chunks of a peer alternate between `lanes` streams:
+               // the data of chunk c + 1 moves while chunk c completes.  The arrival flags are monotonic sequence numbers,
+               // so the flag of chunk c + 1 is chained behind the flag of chunk c with an event.
+               for (int k = 1; k < np; k++) {
+                  const int m = (me + k) % np;
+                  const int prank = nf.peers[k - 1];
+                  cudaStream_t cs = ctx->copy_stream_for((k - 1) * lanes + c % lanes);
                   LinkChunk R; // the consumer side ON THE DESTINATION rank: where it expects this rank's block
                   fft_link_chunk(dpeer[m], nxt, pen, padq, b[c], b[c + 1], R);
                   D2D_REQUIRE(R.cnt[me] == S.cnt[m], "pipelined chain: chunk sizes of the two sides disagree");
@@ -317,12 +389,23 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
                   if (c == 0) {
                      p2p_wait(ctx, prank, 0, epoch, cs);
                      if (ctx->profiling) ctx->prof_begin(names[pen][nxt], 0, spans[k], cs);
+                     if (lanes > 1) { // the other lanes may write into the peer once lane 0 has seen its "ready"
+                        ready_seen[k] = ctx->new_sync_event();
+                        D2D_CHECK_CUDA(cudaEventRecord(ready_seen[k], cs));
+                     }
+                  } else if (c < lanes) {
+                     D2D_CHECK_CUDA(cudaStreamWaitEvent(cs, ready_seen[k], 0));
                   }
                   char *dst = (char *)p2p_peer_work(ctx, recv_w, prank);
                   const size_t off = (size_t)es * R.off[me], nbytes = (size_t)es * S.cnt[m];
                   D2D_REQUIRE(dst != nullptr && off + nbytes <= p2p_peer_bytes(ctx, recv_w, prank), "pipelined chain: destination buffer too small");
                   if (nbytes) D2D_CHECK_CUDA(cudaMemcpyAsync(dst + off, (const char *)sendbuf + (size_t)es * S.off[m], nbytes, cudaMemcpyDefault, cs));
+                  if (lanes > 1 && c > 0) D2D_CHECK_CUDA(cudaStreamWaitEvent(cs, flagged[k], 0)); // flag of chunk c - 1 first
                   p2p_signal(ctx, prank, 2, nf.seq_base + (uint32_t)c + 1, cs);
+                  if (lanes > 1 && c + 1 < K) {
+                     flagged[k] = ctx->new_sync_event();
+                     D2D_CHECK_CUDA(cudaEventRecord(flagged[k], cs));
+                  }
                   if (ctx->profiling) {
                      ctx->prof[spans[k].idx].bytes += (double)nbytes;
                      if (c == K - 1) ctx->prof_end(spans[k], cs);
@@ -349,7 +432,8 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
                nf.arrived.push_back(e);
             }
          }
-         if (ce) ctx->mark_buffer_busy(send_w, np - 1);
+         if (sm) ctx->mark_buffer_busy_on(send_w, ctx->push_stream);
+         else if (ce) ctx->mark_buffer_busy(send_w, (np - 1) * lanes);
          else { // the communication stream still reads the send buffer: the next writer of it waits for that
             if (ctx->buf_busy[send_w].empty()) {
                cudaEvent_t e;
@@ -384,10 +468,17 @@ static void run_chain_pipe(Plan &p, const Decomp &dc, const Decomp *dr, const St
 static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDef st[3], void *in, void *out, int backward)
 {
    Ctx *ctx = p.ctx;
-   // multi-rank: the chunk-pipelined chain (copy-engine pushes over peer memory, or the transport's exchange); D2D_FUSED=1
-   // selects the round-1 variant whose producer kernels store straight into the peers' buffers (no chunks, no copy engines),
-   // D2D_CHUNKS=0 the plain stage -> exchange -> stage sequence on the transport
-   static const bool fused = getenv("D2D_FUSED") && atoi(getenv("D2D_FUSED")) != 0;
+   // Multi-rank chains over peer memory (D2D_EXCHANGE = auto | pipe | fused):
+   //   pipe  : chunk-pipelined chain, the chunks pushed by the copy engines (run_chain_pipe)
+   //   fused : the producer kernels store straight into the peers' buffers, no chunks (run_chain_p2p)
+   // auto picks by measurement (1024^3 fp64 pair on B200s, profiles/r02_*): with one peer per link the copy engines move a
+   // chunk at 690-780 GB/s while the SMs run HBM-bound stages (2 GPUs 10.9 vs 12.9 ms fused, 4 GPUs 7.6 vs 8.4); with three
+   // peers per link every cudaMemcpyAsync carries ~35 us of dead time and the chunks of the three peers serialise on the
+   // engine (500 GB/s), so the fused stores -- 650-670 GB/s of the ~715 GB/s SM-issued writes reach on NVLink -- win
+   // (8 GPUs 5.2 vs 6.1 ms).  Without peer memory (D2D_P2P=0, in-process groups) the pipelined chain runs on the transport;
+   // D2D_CHUNKS=0 selects the plain stage -> exchange -> stage sequence there.
+   static const std::string xmode = getenv("D2D_EXCHANGE") ? getenv("D2D_EXCHANGE") : ((getenv("D2D_FUSED") && atoi(getenv("D2D_FUSED")) != 0) ? "fused" : "auto");
+   const bool fused = xmode == "fused" || (xmode == "auto" && std::max(ctx->p_row, ctx->p_col) > 2);
    if (p2p_active(ctx) && fused) return run_chain_p2p(p, dc, dr, st, in, out, backward);
    const char *ck = getenv("D2D_CHUNKS") ? getenv("D2D_CHUNKS") : getenv("D2D_OVERLAP");
    const bool plain = ck && atoi(ck) <= 0;

@@ -44,11 +44,12 @@ struct P2P {
    void *peer_work[kWorkBuffers][kMaxRanks] = {};
    size_t peer_bytes[kWorkBuffers][kMaxRanks] = {};
    void *opened[kWorkBuffers][kMaxRanks] = {};
-   uint32_t *flags = nullptr; // local: [0..nranks) ready_from, [nranks..2 nranks) done_from, [2 nranks..3 nranks) arrived_from
+   uint32_t *flags = nullptr; // local: [0..nranks) ready_from, [nranks..2 nranks) done_from, [2 nranks..3 nranks) arrived_from (chunk sequence numbers), [3 nranks..4 nranks) pushed_from (counters)
    uint32_t *peer_flags[kMaxRanks] = {};
    void *opened_flags[kMaxRanks] = {};
    bool flags_published = false;
    uint32_t epoch = 0, seq = 0;
+   uint32_t pushes_expected[kMaxRanks] = {};
    WriteValueFn write_value = nullptr;
    WaitValueFn wait_value = nullptr;
 };
@@ -88,13 +89,14 @@ void p2p_publish(Ctx *ctx)
       ctx->p2p->rank = ctx->rank;
       ctx->p2p->write_value = (WriteValueFn)driver_fn("cuStreamWriteValue32");
       ctx->p2p->wait_value = (WaitValueFn)driver_fn("cuStreamWaitValue32");
-      D2D_CHECK_CUDA(cudaMalloc((void **)&ctx->p2p->flags, 3 * kMaxRanks * sizeof(uint32_t)));
-      D2D_CHECK_CUDA(cudaMemset(ctx->p2p->flags, 0, 3 * kMaxRanks * sizeof(uint32_t)));
+      D2D_CHECK_CUDA(cudaMalloc((void **)&ctx->p2p->flags, 4 * kMaxRanks * sizeof(uint32_t)));
+      D2D_CHECK_CUDA(cudaMemset(ctx->p2p->flags, 0, 4 * kMaxRanks * sizeof(uint32_t)));
    }
    P2P *p = ctx->p2p;
    D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-   for (int k = 0; k < kMaxP; k++)
+   for (int k = 0; k < 2 * kMaxP; k++)
       if (ctx->copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_stream[k]));
+   if (ctx->push_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->push_stream));
    close_work(p);
    Published mine;
    memset(&mine, 0, sizeof(mine));
@@ -149,8 +151,9 @@ void p2p_unpublish(Ctx *ctx)
    P2P *p = ctx->p2p;
    if (!p || ctx->nranks <= 1 || !ctx->tr) return;
    D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-   for (int k = 0; k < kMaxP; k++)
+   for (int k = 0; k < 2 * kMaxP; k++)
       if (ctx->copy_stream[k]) D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_stream[k]));
+   if (ctx->push_stream) D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->push_stream));
    close_work(p);
    p->ok = false;
    int one = 1;
@@ -172,6 +175,14 @@ uint32_t p2p_reserve_seq(Ctx *ctx, uint32_t n)
    ctx->p2p->seq += n;
    return base;
 }
+
+uint32_t p2p_expect_push(Ctx *ctx, int peer)
+{
+   P2P *p = ctx->p2p;
+   p->pushes_expected[peer] += (uint32_t)push_ctas();
+   return p->pushes_expected[peer];
+}
+uint32_t *p2p_push_flag(Ctx *ctx, int peer) { return ctx->p2p->peer_flags[peer] + 3 * ctx->p2p->nranks + ctx->p2p->rank; }
 
 // tell `peer` that stream `st` of this rank (default: the context's stream) reached the point `which` with `value`
 void p2p_signal(Ctx *ctx, int peer, int which, uint32_t value, cudaStream_t st)
