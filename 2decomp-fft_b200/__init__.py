@@ -280,22 +280,32 @@ class Decomp2d:
         _check(lib().d2d_decomp_create(self._h, nx, ny, nz, C.byref(h)))
         return DecompInfo(h, *self.dims)
 
-    # alloc_x / alloc_y / alloc_z (src/alloc.f90:10-134): pencil-shaped array, Fortran order
-    def _alloc(self, pencil, dtype, decomp):
+    # alloc_x / alloc_y / alloc_z (src/alloc.f90:10-134; device arrays: src/alloc_dev.f90): pencil-shaped array, Fortran order.
+    # opt_levels = halo cells added on both sides of each dimension (alloc.f90:39-59 via opt_levels); opt_global = the
+    # Fortran array would be indexed with global bounds (xstart:xend): recorded as the `lbound` attribute of the tensor, whose
+    # element [0,0,0] is then global point lbound (1-based, like the reference), otherwise lbound = (1,1,1) - levels.
+    def _alloc(self, pencil, dtype, decomp, opt_global=False, opt_levels=None):
         torch = _torch()
         d = decomp or self.decomp_main
-        n1, n2, n3 = (d.xsz, d.ysz, d.zsz)[pencil]
+        lv = tuple(int(v) for v in (opt_levels if opt_levels is not None else (0, 0, 0)))
+        if len(lv) != 3 or min(lv) < 0:
+            raise Decomp2dError(2, "opt_levels must be three non-negative integers")
+        sz = (d.xsz, d.ysz, d.zsz)[pencil]
+        st = (d.xst, d.yst, d.zst)[pencil]
+        n1, n2, n3 = [sz[i] + 2 * lv[i] for i in range(3)]
         base = torch.zeros((n3, n2, n1), dtype=dtype, device=f"cuda:{self.device}")
-        return base.permute(2, 1, 0)
+        t = base.permute(2, 1, 0)
+        t.lbound = tuple((st[i] if opt_global else 1) - lv[i] for i in range(3))
+        return t
 
-    def alloc_x(self, dtype, decomp=None):
-        return self._alloc(0, dtype, decomp)
+    def alloc_x(self, dtype, decomp=None, opt_global=False, opt_levels=None):
+        return self._alloc(0, dtype, decomp, opt_global, opt_levels)
 
-    def alloc_y(self, dtype, decomp=None):
-        return self._alloc(1, dtype, decomp)
+    def alloc_y(self, dtype, decomp=None, opt_global=False, opt_levels=None):
+        return self._alloc(1, dtype, decomp, opt_global, opt_levels)
 
-    def alloc_z(self, dtype, decomp=None):
-        return self._alloc(2, dtype, decomp)
+    def alloc_z(self, dtype, decomp=None, opt_global=False, opt_levels=None):
+        return self._alloc(2, dtype, decomp, opt_global, opt_levels)
 
     def _transpose(self, direction, src, dst, decomp):
         d = decomp or self.decomp_main
@@ -412,6 +422,7 @@ class Decomp2dFFTEngine:
         self.nz_fft = d2d.nz_global if nz is None else nz
         self.dtype = torch.float64 if dtype is None else dtype
         self.inplace = bool(opt_inplace)
+        self.inplace_r2c = self.inplace_c2r = False  # never supported by this backend (checked above), like cuFFT's
         skip = list(opt_skip_XYZ_c2c) if opt_skip_XYZ_c2c is not None else [False] * 3
         self.skip_x_c2c, self.skip_y_c2c, self.skip_z_c2c = [bool(s) for s in skip]
         cskip = (C.c_int * 3)(*[int(bool(s)) for s in skip])
@@ -451,7 +462,7 @@ class Decomp2dFFTEngine:
         _check_dtype(inp, self.dtype, "in")
         _check_dtype(out, self.dtype, "out")
         if inp.data_ptr() == out.data_ptr() and inp.numel():
-            raise Decomp2dError(2, "decomp_2d_fft_3d: in and out must be different arrays (the input is preserved)")
+            raise Decomp2dError(2, "decomp_2d_fft_3d: the input and output arrays overlap")
         if inp.is_complex() and out.is_complex():
             if isign not in (DECOMP_2D_FFT_FORWARD, DECOMP_2D_FFT_BACKWARD):
                 raise Decomp2dError(1, "c2c transforms need isign = DECOMP_2D_FFT_FORWARD / _BACKWARD")
@@ -495,6 +506,7 @@ def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, d
                           allgather=allgather)
     _state.engines = {}
     _state.current = None
+    _state.n_grid = 0
     return _state.d2d
 
 
@@ -555,20 +567,44 @@ def transpose_y_to_x(src, dst, decomp=None):
     _cur().transpose_y_to_x(src, dst, decomp)
 
 
-def alloc_x(dtype, decomp=None):
-    return _cur().alloc_x(dtype, decomp)
+def alloc_x(dtype, decomp=None, opt_global=False, opt_levels=None):
+    return _cur().alloc_x(dtype, decomp, opt_global, opt_levels)
 
 
-def alloc_y(dtype, decomp=None):
-    return _cur().alloc_y(dtype, decomp)
+def alloc_y(dtype, decomp=None, opt_global=False, opt_levels=None):
+    return _cur().alloc_y(dtype, decomp, opt_global, opt_levels)
 
 
-def alloc_z(dtype, decomp=None):
-    return _cur().alloc_z(dtype, decomp)
+def alloc_z(dtype, decomp=None, opt_global=False, opt_levels=None):
+    return _cur().alloc_z(dtype, decomp, opt_global, opt_levels)
 
 
-def decomp_2d_fft_init(pencil=PHYSICAL_IN_X, nx=None, ny=None, nz=None, igrid=1, **opts):
-    """decomp_2d_fft_init, all four overloads (src/fft_common.f90:42-138)."""
+# decomp_2d_fft_set_ngrid / _get_ngrid (src/fft_common.f90:368-413): the number of FFT engines the module keeps.  Engines
+# that exist survive a resize (up to the new count), like the move_alloc of the reference.
+def decomp_2d_fft_set_ngrid(ngrd):
+    _cur()
+    if ngrd < 1:
+        raise Decomp2dError(ngrd, "Invalid value for n_grid")
+    engines = getattr(_state, "engines", {})
+    for ig in [k for k in engines if k > ngrd]:
+        engines.pop(ig).fin()
+    _state.engines = engines
+    _state.n_grid = ngrd
+
+
+def decomp_2d_fft_get_ngrid():
+    return getattr(_state, "n_grid", 0)
+
+
+def decomp_2d_fft_init(pencil=PHYSICAL_IN_X, nx=None, ny=None, nz=None, igrid=None, **opts):
+    """decomp_2d_fft_init, all four overloads (src/fft_common.f90:42-138): without igrid ONE engine is kept
+    (fft_init_one_grid: set_ngrid(1), engine 1); with igrid the engine of that grid is (re)initialised
+    (fft_init_multiple_grids; decomp_2d_fft_set_ngrid must have been called)."""
+    if igrid is None:
+        decomp_2d_fft_set_ngrid(1)
+        igrid = 1
+    elif igrid < 1 or igrid > decomp_2d_fft_get_ngrid():
+        raise Decomp2dError(igrid, "Invalid value for igrid")
     eng = Decomp2dFFTEngine(_cur(), pencil, nx, ny, nz, **opts)
     old = _state.engines.get(igrid)
     if old is not None:
@@ -578,36 +614,67 @@ def decomp_2d_fft_init(pencil=PHYSICAL_IN_X, nx=None, ny=None, nz=None, igrid=1,
     return eng
 
 
+def _grid_engine(igrid):
+    n = decomp_2d_fft_get_ngrid()
+    if n < 1:
+        raise Decomp2dError(n, "The FFT module was not initialised")
+    if igrid < 1 or igrid > n:
+        raise Decomp2dError(igrid, "Invalid value for igrid")
+    eng = _state.engines.get(igrid)
+    if eng is None or not eng._h:
+        raise Decomp2dError(-1, "FFT engine is not ready")
+    return eng
+
+
+# decomp_2d_fft_use_grid (src/fft_common.f90:418-443) -> engine%use_it (:446-479)
 def decomp_2d_fft_use_grid(igrid=1):
-    _state.current = _state.engines[igrid]
+    _state.current = _grid_engine(igrid)
     return _state.current
 
 
+# decomp_2d_fft_get_engine (src/fft_common.f90:485-511)
 def decomp_2d_fft_get_engine(igrid=1):
-    return _state.engines[igrid]
+    return _grid_engine(igrid)
 
 
-def decomp_2d_fft_3d(inp, out, isign=None):
+def _current_engine():
     eng = getattr(_state, "current", None)
     if eng is None:
         raise Decomp2dError(1, "decomp_2d_fft_init has not been called")
-    eng.fft_3d(inp, out, isign)
+    return eng
+
+
+def decomp_2d_fft_3d(inp, out, isign=None):
+    _current_engine().fft_3d(inp, out, isign)
 
 
 def decomp_2d_fft_get_size():
-    return _state.current.get_size()
+    return _current_engine().get_size()
 
 
 def decomp_2d_fft_get_ph():
-    return _state.current.ph
+    return _current_engine().ph
 
 
 def decomp_2d_fft_get_sp():
-    return _state.current.sp
+    return _current_engine().sp
 
 
 def decomp_2d_fft_get_format():
-    return _state.current.format
+    return _current_engine().format
+
+
+# src/fft_common.f90:525-555
+def decomp_2d_fft_get_inplace():
+    return _current_engine().inplace
+
+
+def decomp_2d_fft_get_inplace_r2c():
+    return _current_engine().inplace_r2c
+
+
+def decomp_2d_fft_get_inplace_c2r():
+    return _current_engine().inplace_c2r
 
 
 def decomp_2d_fft_finalize():
@@ -615,3 +682,4 @@ def decomp_2d_fft_finalize():
         eng.fin()
     _state.engines = {}
     _state.current = None
+    _state.n_grid = 0

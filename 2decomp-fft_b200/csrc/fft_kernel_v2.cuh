@@ -121,6 +121,14 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
                 : "memory");
 }
 
+// two adjacent complex values as ONE store (the spectra of a real line pair that are neighbours in memory): 256-bit STG for
+// fp64 (sm_100: st.global.v4.f64), 128-bit for fp32 -- instead of two stores that each fill half of every 32-byte sector
+__device__ __forceinline__ void store_pair(double2 *q, double2 a, double2 b)
+{
+   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(q), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+__device__ __forceinline__ void store_pair(float2 *q, float2 a, float2 b) { *reinterpret_cast<float4 *>(q) = make_float4(a.x, a.y, b.x, b.y); }
+
 // One pass with the compact twiddle layout (otherwise PassOp's).
 template <typename T, class P, int PASS, int SP, int PADK> struct PassOp2 : PassOp<T, P, PASS, SP, PADK, true> {
    using Base = PassOp<T, P, PASS, SP, PADK, true>;
@@ -523,8 +531,20 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
 
       // ------------------------------------------------------------------ transform
       bool late_done = false;
+      // C2R of a tile-like input writes real lines that are contiguous in memory (c2r_x of PHYSICAL_IN_X): straight from the
+      // registers a warp would store 8-real runs of 8 different lines (64 / 32 bytes each), so the lines are staged through
+      // the exchange buffer and leave as 512-byte runs.  The late half of the next tile is requested after that instead of
+      // after the last exchange.
+      constexpr int SPITCH = N + 16 / (int)sizeof(T); // reals per staged line (+16 bytes: the lines a half-warp writes fall into distinct banks)
+      // fp32 only: 2.99 -> 1.72 ms at 1024^3 (32-byte runs before); fp64 loses (3.6 -> 4.6 ms: its 64-byte runs were tolerable
+      // and the late half of the next tile, requested only after the staging, is no longer hidden behind the last pass)
+      constexpr bool CAN_SOUT = (MODE == MODE_C2R && INL == IN_TILE && !MRG && sizeof(T) == 4 && (size_t)2 * TX * SPITCH * sizeof(T) <= G::x_sub);
+      const bool sout = CAN_SOUT && g.rse == 1;
       if (!g.passthrough) {
          if constexpr (MODE == MODE_R2C && !G::mirror_fits) {
+            auto nolate = [&]() {};
+            RunPasses2<T, P, 0, SP, PADK, decltype(nolate)>::run(v, j, lsm, tws, nolate);
+         } else if (CAN_SOUT && sout) {
             auto nolate = [&]() {};
             RunPasses2<T, P, 0, SP, PADK, decltype(nolate)>::run(v, j, lsm, tws, nolate);
          } else {
@@ -558,6 +578,37 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
             }
          }
       } else if constexpr (MODE == MODE_C2R) {
+         if (CAN_SOUT && sout) {
+            __syncthreads(); // the last exchange has been read by everybody: the buffer is free (no late landing requested yet)
+            T *stg = reinterpret_cast<T *>(Xbase + (size_t)ly * G::x_sub);
+#pragma unroll
+            for (int s = 0; s < E; s++) {
+               stg[(2 * tx) * SPITCH + j + TPL * s] = v[s].x;
+               stg[(2 * tx + 1) * SPITCH + j + TPL * s] = -v[s].y;
+            }
+            __syncthreads();
+            constexpr int NW = TX * LY * TPL / 32, VW = 16 / (int)sizeof(T);
+            const int warp = tid / 32, lane = tid % 32;
+            if (!(g.debug & 1)) {
+               for (int l = warp; l < LY * 2 * TX; l += NW) {
+                  const int sl = l / (2 * TX), ll = l % (2 * TX);
+                  const int tile = grp * LY + sl;
+                  if (tile >= ntiles) continue;
+                  const int bb = tile / tiles_a;
+                  const long long ar = 2LL * ((tile - bb * tiles_a) * TX + ll / 2) + (ll & 1);
+                  if (ar >= g.na_real) continue;
+                  T *dst = reinterpret_cast<T *>(g.rptr) + ar * g.rsa + (long long)bb * g.rsb;
+                  const T *src = reinterpret_cast<const T *>(Xbase + (size_t)sl * G::x_sub) + ll * SPITCH;
+                  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                     for (int c = lane * VW; c < N; c += 32 * VW) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(src + c);
+                  } else {
+                     for (int c = lane; c < N; c += 32) dst[c] = src[c];
+                  }
+               }
+            }
+            late(); // fence + barrier, then the late half of the next tile may land in the buffer
+            continue;
+         }
          if (!late_done) late();
          // real output: element e of real line ar at rptr + e rse + ar rsa + b rsb; lines 2a, 2a+1 of this thread
          T *__restrict__ rp = reinterpret_cast<T *>(g.rptr) + (long long)j * g.rse + (long long)(2 * a) * g.rsa + (long long)b * g.rsb;
@@ -618,8 +669,11 @@ __global__ void __launch_bounds__(TX *LY *P::T, MINB) fft_kernel_v2(const __grid
                   T2 A = T2{(zk.x + zn[s].x) * hf, (zk.y - zn[s].y) * hf};
                   T2 B = T2{(zk.y + zn[s].y) * hf, (zn[s].x - zk.x) * hf};
                   T2 *q = cur.at(k);
-                  *q = A;
-                  if (v1) q[cur.sa()] = B;
+                  if (v1 && cur.sa() == 1 && (reinterpret_cast<uintptr_t>(q) & (2 * sizeof(T2) - 1)) == 0) store_pair(q, A, B);
+                  else {
+                     *q = A;
+                     if (v1) q[cur.sa()] = B;
+                  }
                }
             }
          }

@@ -64,8 +64,12 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    g.out = out;
    g.backward = backward;
    g.passthrough = passthrough;
+#ifdef D2D_DEBUG_KNOBS // experiments only (make EXTRA=-DD2D_DEBUG_KNOBS): kernels that drop their loads / stores return garbage
    static const int dbg = getenv("D2D_DEBUG_SKIP") ? atoi(getenv("D2D_DEBUG_SKIP")) : 0;
    g.debug = dbg;
+#else
+   g.debug = 0;
+#endif
    g.sm_limit = ctx->fft_grid_limit;
    int kind;
    if (chain) {
@@ -488,6 +492,10 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
    const size_t wbytes = uniform_work_bytes(p, dr == nullptr);
    // `out` can stand in for the first work buffer only when the padded wire layout fits in it
    const bool borrow_out = (ctx->nranks == 1) && st[2].mode == MODE_C2C && wbytes <= (size_t)es * dc.pencil_elems(st[2].pencil);
+   // opt_inplace (src/fft_common.f90:172-176, src/fft_cufft.f90:696-706, 961-971): a complex input may be overwritten -- it
+   // then serves as the work buffer between stages 1 and 2, so a single-rank c2c whose padded wire layout fits the pencils
+   // needs no work buffer at all (out carries link 0, in carries link 1)
+   const bool reuse_in = p.inplace && ctx->nranks == 1 && st[0].mode != MODE_R2C && wbytes <= (size_t)es * dc.pencil_elems(st[0].pencil);
    int live_a = -1, live_b = -1; // work buffers holding the current stage's input
    auto pick = [&]() {
       for (int i = 0; i < 3; i++)
@@ -508,6 +516,7 @@ static void run_chain(Plan &p, const Decomp &dc, const Decomp *dr, const StageDe
          else om = fft_user_map(dc, pen, out);
       } else {
          if (s == 0 && borrow_out) sendbuf = out;
+         else if (s == 1 && reuse_in) sendbuf = in; // opt_inplace: stage 0 has consumed the user's input (stream order)
          else { send_w = pick(); sendbuf = ctx->reserve(send_w, wbytes); }
          om = fft_link_map(dc, pen, st[s + 1].pencil, sendbuf, sendbuf, es, false, padq);
       }
@@ -651,7 +660,10 @@ static void run_chain_p2p(Plan &p, const Decomp &dc, const Decomp *dr, const Sta
 static void ensure_work(Plan &p, bool c2c, bool at_plan_creation)
 {
    Ctx *ctx = p.ctx;
-   ctx->ensure_buffers(ctx->nranks > 1 ? kCtxBuffers : 2, uniform_work_bytes(p, c2c), at_plan_creation);
+   // one rank: run_chain reserves what it needs when it needs it (nothing at all for an in-place c2c whose wire layout fits
+   // the user's arrays); several ranks: the buffers are mapped between the ranks, so they are sized and published here
+   if (ctx->nranks == 1) return;
+   ctx->ensure_buffers(kCtxBuffers, uniform_work_bytes(p, c2c), at_plan_creation);
 }
 
 Plan *plan_create(Ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3])
@@ -689,10 +701,23 @@ void plan_destroy(Plan *p)
 const d2d_decomp *plan_ph(const Plan *p) { return &p->ph; }
 const d2d_decomp *plan_sp(const Plan *p) { return &p->sp; }
 
+static void plan_bytes(const Plan *p, size_t b[4], int isign);
+// in and out of a 3-D transform are different pencils; the stages write `out` (and, in place, `in`) while `in` is still being
+// read, so overlapping arrays would be silently corrupted: refuse them
+static void require_disjoint(const Plan *p, const void *in, int bi, const void *out, int bo, int isign)
+{
+   size_t b[4];
+   plan_bytes(p, b, isign);
+   const char *a = (const char *)in, *o = (const char *)out;
+   D2D_REQUIRE(a != nullptr && o != nullptr, "null array");
+   D2D_REQUIRE(a + b[bi] <= o || o + b[bo] <= a, "decomp_2d_fft_3d: the input and output arrays overlap");
+}
+
 // fft_3d_c2c (src/fft_cufft.f90:676-790): X-forward / Z-backward run x -> y -> z, the others z -> y -> x
 void fft_3d_c2c(Plan *p, void *in, void *out, int isign)
 {
    D2D_REQUIRE(isign == D2D_FFT_FORWARD || isign == D2D_FFT_BACKWARD, "isign must be -1 or +1");
+   require_disjoint(p, in, 2, out, 3, isign);
    D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
    ensure_work(*p, true, false); // first c2c call of this context: grows the work buffers to the ph-complex size (collective)
    ProfScope ps(p->ctx, "fft_c2c");
@@ -706,6 +731,7 @@ void fft_3d_c2c(Plan *p, void *in, void *out, int isign)
 // fft_3d_r2c (src/fft_cufft.f90:795-934)
 void fft_3d_r2c(Plan *p, const void *in_r, void *out_c)
 {
+   require_disjoint(p, in_r, 0, out_c, 1, D2D_FFT_FORWARD);
    D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
    ProfScope ps(p->ctx, "fft_r2c");
    const StageDef x[3] = {{0, MODE_R2C}, {1, MODE_C2C}, {2, MODE_C2C}};
@@ -716,6 +742,7 @@ void fft_3d_r2c(Plan *p, const void *in_r, void *out_c)
 // fft_3d_c2r (src/fft_cufft.f90:939-1170)
 void fft_3d_c2r(Plan *p, void *in_c, void *out_r)
 {
+   require_disjoint(p, in_c, 1, out_r, 0, D2D_FFT_BACKWARD);
    D2D_CHECK_CUDA(cudaSetDevice(p->ctx->device));
    ProfScope ps(p->ctx, "fft_c2r");
    const StageDef x[3] = {{2, MODE_C2C}, {1, MODE_C2C}, {0, MODE_C2R}};
@@ -868,15 +895,19 @@ void fft_3d_host(Plan *p, int which /*0 r2c, 1 c2r, 2 c2c*/, const void *in_h, v
    }
    if (pin != 0) gate.need_in(0, bi); // the whole input first
    p->gate = &gate;
+   const int keep_inplace = p->inplace;
+   p->inplace = 1; // the staging copy of the input may be clobbered
    try {
       if (which == 0) fft_3d_r2c(p, io.in, io.out);
       else if (which == 1) fft_3d_c2r(p, io.in, io.out);
       else fft_3d_c2c(p, io.in, io.out, isign);
    } catch (...) {
       p->gate = nullptr;
+      p->inplace = keep_inplace;
       throw;
    }
    p->gate = nullptr;
+   p->inplace = keep_inplace;
    D2D_CHECK_CUDA(cudaEventRecord(io.in_done, st));
    if (pout != 0 || ht.d2h_cut.empty()) download(0, bo); // not announced slab by slab: the whole output now
    if (dspan_open) ctx->prof_end(dspan, dn);

@@ -11,7 +11,7 @@ import pytest
 from util import ROOT
 
 
-def test_c_example_builds_links_and_reports_errors(tmp_path):
+def _build_and_run(tmp_path):
     cxx = shutil.which("g++")
     if cxx is None:
         pytest.skip("g++ not available")
@@ -32,3 +32,14 @@ def test_c_example_builds_links_and_reports_errors(tmp_path):
         assert r.returncode == 0 and "fft_r2c_z completed" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 1 and "error" in r.stderr and "cudaSetDevice" in r.stderr, r.stdout + r.stderr
+
+
+def test_c_example_builds_links_and_reports_errors(tmp_path):
+    _build_and_run(tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    """the compiled C++ host on the device: d2d_dev_alloc, d2d_host_alloc_pinned, d2d_host_get_device_pointer, d2d_memcpy(_async),
+    the device-pointer and the host-array 3-D entry points"""
+    _build_and_run(tmp_path)

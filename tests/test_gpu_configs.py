@@ -138,7 +138,8 @@ def _max_abs_diff(a, b, planes=16):
 
 @pytest.mark.parametrize("case", ["1024_f64_z", "2048_f32_x"])
 def test_full_size_properties(case):
-    """round trip and Parseval at the sizes of configs[3] / configs[4] on a 1 x 1 grid (the oracle cannot reach them);
+    """configs[3] / configs[4] at full size on a 1 x 1 grid: the forward spectrum of a separable seeded field against the
+    oracle's 1-D transforms of its factor lines (all bins), then round trip and Parseval of a random field;
     c2r writes back into the input array and the input is regenerated from its seed for the comparison."""
     import torch
     p = pkg()
@@ -155,6 +156,34 @@ def test_full_size_properties(case):
     alloc_in, alloc_out = (d2d.alloc_z, d2d.alloc_x) if fmt == p.PHYSICAL_IN_Z else (d2d.alloc_x, d2d.alloc_z)
     a = alloc_in(rdt, eng.ph)
     spec = alloc_out(cdt, eng.sp)
+    # (1) forward spectrum against ORACLE lines: a separable random field f = fa(i) fb(j) fc(k) has the spectrum
+    #     A(kx) B(ky) C(kz), where A, B, C are the oracle's (Glassman) 1-D transforms of the three seeded factor lines --
+    #     every bin of the full-size spectrum is compared, at the cost of three oracle lines
+    rng = np.random.default_rng(20240601)
+    fac = [rng.uniform(-1, 1, n) for _ in range(3)]
+    half_axis = 2 if fmt == p.PHYSICAL_IN_Z else 0
+    lines = []
+    for ax in range(3):
+        col = np.asfortranarray(fac[ax].reshape(n, 1, 1))
+        if ax == half_axis:
+            lines.append(orc.r2c_1m(col, 0).reshape(-1))
+        else:
+            lines.append(orc.c2c_1m(col.astype(np.complex128), 0, orc.FORWARD).reshape(-1))
+    dev = a.device
+    tf = [torch.from_numpy(f).to(dev) for f in fac]
+    plane = tf[0][:, None] * tf[1][None, :]
+    for k in range(n):
+        a[:, :, k] = (plane * tf[2][k]).to(rdt)
+    eng.fft_3d(a, spec)
+    tl = [torch.from_numpy(l).to(dev) for l in lines]
+    refmax = float(tl[0].abs().max() * tl[1].abs().max() * tl[2].abs().max())
+    rp = tl[0][:, None] * tl[1][None, :]
+    worst = 0.0
+    for k in range(spec.shape[2]):
+        worst = max(worst, float((spec[:, :, k].to(torch.complex128) - rp * tl[2][k]).abs().max().item()))
+    assert worst / refmax < (1e-12 if prec == "f64" else 1e-5), worst / refmax
+    del plane, rp
+    # (2) size-independent properties of a random field
     gen = torch.Generator(device=a.device)
     gen.manual_seed(20240601)
     a.uniform_(-1, 1, generator=gen)
