@@ -106,6 +106,9 @@ def lib():
         l.d2d_decomp_query.argtypes = [C.c_void_p] * 10
         l.d2d_decomp_dist.argtypes = [C.c_void_p] * 5
         l.d2d_decomp_counts.argtypes = [C.c_void_p] * 9
+        l.d2d_decomp_even.argtypes = [C.c_void_p] * 6
+        l.d2d_halo_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.d2d_ctx_set_even.argtypes = [C.c_void_p, C.c_int]
         l.d2d_fft_plan_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.d2d_fft_plan_destroy.argtypes = [C.c_void_p]
         l.d2d_fft_plan_ph.argtypes = [C.c_void_p, C.c_void_p]
@@ -152,6 +155,11 @@ class DecompInfo:
              (C.c_int64 * p_row)(), (C.c_int64 * p_row)(), (C.c_int64 * p_col)(), (C.c_int64 * p_col)()]
         _check(l.d2d_decomp_counts(handle, *c))
         (self.x1cnts, self.y1cnts, self.y2cnts, self.z2cnts, self.x1disp, self.y1disp, self.y2disp, self.z2disp) = [tuple(x) for x in c]
+        e = [C.c_int64() for _ in range(4)]
+        ev = C.c_int()
+        _check(l.d2d_decomp_even(handle, *[C.byref(v) for v in e], C.byref(ev)))
+        self.x1count, self.y1count, self.y2count, self.z2count = [v.value for v in e]  # EVEN builds (decomp_2d.f90:1197-1203)
+        self.even = bool(ev.value)
 
     @classmethod
     def for_rank(cls, nx, ny, nz, p_row, p_col, rank):
@@ -243,7 +251,8 @@ def _check_pencil(t, shape, what):
 class Decomp2d:
     """One rank's library state: what decomp_2d_init sets up (src/decomp_2d_init_fin.f90:15-184)."""
 
-    def __init__(self, nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None):
+    def __init__(self, nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None,
+                 periodic_bc=None):
         """unique_id: NCCL bootstrap (d2d_ctx_create); group: thread-per-rank ranks of one process; allgather: a callable
         bytes -> [bytes per rank] (MPI_Allgather-like) for the NCCL-free bootstrap (d2d_ctx_create_bootstrap)."""
         torch = _torch()
@@ -255,6 +264,8 @@ class Decomp2d:
         self.device = device
         self._h = C.c_void_p()
         self._allgather_cb = None
+        # periodic_bc of decomp_2d_init (src/decomp_2d_init_fin.f90:31-41): only the halo exchange looks at it
+        self.periodic_bc = tuple(bool(v) for v in (periodic_bc if periodic_bc is not None else (False, False, False)))
         if group is not None:
             _check(l.d2d_ctx_create_in_group(C.byref(self._h), group._h, rank, p_row, p_col, device))
         elif allgather is not None:
@@ -316,6 +327,34 @@ class Decomp2d:
             raise Decomp2dError(2, "src and dst must have the same type")
         _check(lib().d2d_transpose(self._h, d._h, direction, _dtype_code(src), int(src.is_complex()), src.data_ptr(), dst.data_ptr()))
 
+    # update_halo (src/halo.f90:101-198): returns `out`, the pencil with `level` ghost layers on its two decomposed axes,
+    # interior copied from `in` and ghost layers filled from the neighbouring pencils.  opt_pencil = 1, 2, 3 like the reference
+    # (deduced from the shape when omitted, src/halo.f90:201-245); opt_global only changes the Fortran index bounds of `out`
+    # (recorded as `lbound`).
+    def update_halo(self, inp, level, decomp=None, opt_global=False, opt_pencil=None):
+        torch = _torch()
+        d = decomp or self.decomp_main
+        shp = tuple(inp.shape)
+        if opt_pencil is None:
+            if shp[0] == d.xsz[0]:
+                opt_pencil = 1
+            elif shp[1] == d.ysz[1]:
+                opt_pencil = 2
+            elif shp[2] == d.zsz[2]:
+                opt_pencil = 3
+            else:
+                raise Decomp2dError(1, "Invalid decomposition size")
+        if opt_pencil not in (1, 2, 3):
+            raise Decomp2dError(10, "Invalid data passed to update_halo")
+        pen = opt_pencil - 1
+        _check_pencil(inp, (d.xsz, d.ysz, d.zsz)[pen], "in")
+        lv = [level, level, level]
+        lv[pen] = 0
+        out = self._alloc(pen, inp.dtype, d, opt_global, lv)
+        per = (C.c_int * 3)(*[int(v) for v in self.periodic_bc])
+        _check(lib().d2d_halo_update(self._h, d._h, pen, level, _dtype_code(inp), int(inp.is_complex()), per, inp.data_ptr(), out.data_ptr()))
+        return out
+
     def transpose_x_to_y(self, src, dst, decomp=None):
         self._transpose(X_TO_Y, src, dst, decomp)
 
@@ -370,6 +409,10 @@ class Decomp2d:
 
     def set_blocking(self, flag):
         _check(lib().d2d_ctx_set_blocking(self._h, int(flag)))
+
+    def set_even(self, flag):
+        """bare transposes in the padded equal-count layout of the reference's EVEN builds (same pencils)"""
+        _check(lib().d2d_ctx_set_even(self._h, int(flag)))
 
     def stream(self):
         return lib().d2d_ctx_stream(self._h)
@@ -501,9 +544,10 @@ class Decomp2dFFTEngine:
 _state = threading.local()
 
 
-def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None):
+def decomp_2d_init(nx, ny, nz, p_row, p_col, rank=0, nranks=1, unique_id=None, device=None, group=None, allgather=None,
+                   periodic_bc=None):
     _state.d2d = Decomp2d(nx, ny, nz, p_row, p_col, rank=rank, nranks=nranks, unique_id=unique_id, device=device, group=group,
-                          allgather=allgather)
+                          allgather=allgather, periodic_bc=periodic_bc)
     _state.engines = {}
     _state.current = None
     _state.n_grid = 0
@@ -549,6 +593,10 @@ def decomp_2d_finalize():
 
 def get_decomp_info():
     return _cur().decomp_main
+
+
+def update_halo(inp, level, decomp=None, opt_global=False, opt_pencil=None):
+    return _cur().update_halo(inp, level, decomp, opt_global, opt_pencil)
 
 
 def transpose_x_to_y(src, dst, decomp=None):

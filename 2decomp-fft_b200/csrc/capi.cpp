@@ -19,6 +19,7 @@ void fft_3d_host(Plan *p, int which, const void *in_h, void *out_h, int isign);
 void plan_get_size(const Plan *p, int istart[3], int iend[3], int isize[3]);
 Ctx *plan_ctx(Plan *p);
 void fft_1m(Ctx *ctx, int dtype, int mode, int axis, int n1, int n2, int n3, const void *in, void *out, int isign);
+void halo_update(Ctx *ctx, const Decomp &d, int pencil, int level, int es, const int periodic[3], const void *in, void *out);
 } // namespace d2d
 
 using namespace d2d;
@@ -139,6 +140,11 @@ int d2d_ctx_sync(d2d_ctx *ctx)
 int d2d_ctx_set_blocking(d2d_ctx *ctx, int blocking)
 {
    ctx->c.blocking = blocking != 0;
+   return 0;
+}
+int d2d_ctx_set_even(d2d_ctx *ctx, int even)
+{
+   ctx->c.even = even != 0;
    return 0;
 }
 void *d2d_ctx_stream(d2d_ctx *ctx) { return (void *)ctx->c.stream; }
@@ -265,6 +271,17 @@ int d2d_decomp_counts(const d2d_decomp *h, int64_t *x1cnts, int64_t *y1cnts, int
    return 0;
 }
 
+int d2d_decomp_even(const d2d_decomp *h, int64_t *x1count, int64_t *y1count, int64_t *y2count, int64_t *z2count, int *even)
+{
+   const Decomp &d = h->d;
+   if (x1count) *x1count = d.x1count;
+   if (y1count) *y1count = d.y1count;
+   if (y2count) *y2count = d.y2count;
+   if (z2count) *z2count = d.z2count;
+   if (even) *even = d.even;
+   return 0;
+}
+
 int d2d_transpose(d2d_ctx *ctx, const d2d_decomp *decomp, int direction, int dtype, int is_complex, const void *src, void *dst)
 {
    D2D_TRY
@@ -288,6 +305,16 @@ int d2d_transpose_z_to_y(d2d_ctx *c, const d2d_decomp *d, int dtype, int is_comp
 int d2d_transpose_y_to_x(d2d_ctx *c, const d2d_decomp *d, int dtype, int is_complex, const void *src, void *dst)
 {
    return d2d_transpose(c, d, D2D_Y_TO_X, dtype, is_complex, src, dst);
+}
+
+int d2d_halo_update(d2d_ctx *ctx, const d2d_decomp *decomp, int pencil, int level, int dtype, int is_complex, const int periodic[3],
+                    const void *in, void *out)
+{
+   D2D_TRY
+   D2D_REQUIRE(dtype == D2D_F32 || dtype == D2D_F64, "dtype must be D2D_F32 or D2D_F64");
+   halo_update(&ctx->c, decomp->d, pencil, level, elem_size(dtype, is_complex), periodic, in, out);
+   ctx->c.finish_call();
+   D2D_CATCH
 }
 
 int d2d_fft_plan_create(d2d_ctx *ctx, int format, int nx, int ny, int nz, int dtype, int inplace, const int skip[3], d2d_fft_plan **plan)

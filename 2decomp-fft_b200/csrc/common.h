@@ -50,6 +50,11 @@ struct Decomp {
    int x1off[kMaxP + 1], y1off[kMaxP + 1], y2off[kMaxP + 1], z2off[kMaxP + 1]; // exclusive prefix sums of the dists
    int64_t x1cnts[kMaxP], y1cnts[kMaxP], y2cnts[kMaxP], z2cnts[kMaxP];
    int64_t x1disp[kMaxP], y1disp[kMaxP], y2disp[kMaxP], z2disp[kMaxP];
+   // EVEN builds of the reference (padded MPI_ALLTOALL, src/decomp_2d.f90:1186-1204): one count per communicator, segment m
+   // of a buffer at m * count; `even` = the data is evenly distributed (:443-454)
+   int64_t x1count, y1count, y2count, z2count;
+   int64_t e_cnts_row[kMaxP], e_disp_row[kMaxP], e_cnts_col[kMaxP], e_disp_col[kMaxP]; // x<->y (p_row peers) / y<->z (p_col peers)
+   int even;
    int64_t pencil_elems(int p) const
    {
       const int *s = p == 0 ? xsz : p == 1 ? ysz : zsz;
@@ -103,6 +108,7 @@ struct Ctx {
    cudaStream_t stream = nullptr;
    std::unique_ptr<Transport> tr;
    bool blocking = true;
+   bool even = false; // bare transposes use the padded equal-count layout of the reference's EVEN builds
    int64_t launches = 0;
    // grow-only work buffers (the reference's work1/work2 high-water mark, src/decomp_2d.f90:461-485)
    void *work[kCtxBuffers] = {nullptr, nullptr, nullptr, nullptr};
@@ -185,7 +191,7 @@ struct CopyArgs {
    int ne, na, nb;    // extents of the index space (e: pieces axis, a, b)
    int fast_is_a;     // 1: `a` is the unit-stride axis of both sides, 0: `e` is
 };
-void launch_copy(Ctx *ctx, const CopyArgs &c, int es);
+void launch_copy(Ctx *ctx, const CopyArgs &c, int es, const char *label = nullptr);
 
 // ---- exchange kernel of the pipelined chains (push_kernels.cu) -------------------------------------------------------
 constexpr int kMaxPushSegs = 8;
@@ -211,14 +217,14 @@ inline int elem_size(int dtype, int is_complex) { return (dtype == D2D_F64 ? 8 :
 // piece-map builders.  `es`-agnostic: element units.
 PieceMap natural_map(const Decomp &d, int pencil, void *ptr);
 // send-side map of the transpose leaving pencil `from` towards pencil `to`; the self block stays in `sendbuf`
-PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es);
+PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es, bool even = false);
 // recv-side map for pencil `to` fed from pencil `from`: peers' blocks in recvbuf, own block in sendbuf
-PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es);
+PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es, bool even = false);
 // the exchange itself (peers other than self); element size es
 // send_w / recv_w: indices of the context's work buffers holding sendbuf / recvbuf (-1: a user array); the peer-memory
 // path needs recvbuf == work[recv_w]
-void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w);
-size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es); // largest pencil of any rank of the grid, in bytes
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w, bool even = false);
+size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es, bool even = false); // largest pencil (EVEN: padded buffer) of any rank, in bytes
 int64_t send_total(const Decomp &d, int from, int to);
 int64_t recv_total(const Decomp &d, int from, int to);
 int comm_size(const Decomp &d, int from, int to);

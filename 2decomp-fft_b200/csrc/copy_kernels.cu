@@ -52,10 +52,11 @@ void scale(PieceMap &m, int vw, bool fast_is_a)
 
 } // namespace
 
-void launch_copy(Ctx *ctx, const CopyArgs &c0, int es)
+void launch_copy(Ctx *ctx, const CopyArgs &c0, int es, const char *label)
 {
    CopyArgs c = c0;
    if (c.ne <= 0 || c.na <= 0 || c.nb <= 0) return;
+   ProfScope ps(ctx, label ? label : "copy", 2.0 * es * (double)c.ne * c.na * c.nb); // read + write of the pencil
    // widen to 16-byte (or 8-byte) vectors along the unit-stride axis when every offset allows it
    int vw = 16 / es;
    while (vw > 1) {
@@ -83,4 +84,32 @@ void launch_copy(Ctx *ctx, const CopyArgs &c0, int es)
    ctx->launches++;
 }
 
+} // namespace d2d
+
+// ---- box copies of the halo exchange (halo.cpp) ---------------------------------------------------------------------
+namespace d2d {
+namespace {
+template <typename V> __global__ void __launch_bounds__(256) box_copy_kernel(V *dst, long long d1, long long d12, const V *src, long long s1, long long s12,
+                                                                              int e1, int e2, int e3)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= e1) return;
+   for (int k = blockIdx.z; k < e3; k += gridDim.z)
+      for (int j = blockIdx.y; j < e2; j += gridDim.y) dst[i + d1 * j + d12 * k] = src[i + s1 * j + s12 * k];
+}
+} // namespace
+
+// dst(i, j, k) = src(i, j, k) for a box of (e1, e2, e3) elements of `es` bytes inside two Fortran-ordered arrays with leading
+// dimensions (d1, d2) / (s1, s2); dst and src point at the first element of the box
+void launch_box_copy(Ctx *ctx, void *dst, long long d1, long long d2, const void *src, long long s1, long long s2, int e1, int e2, int e3, int es)
+{
+   if (e1 <= 0 || e2 <= 0 || e3 <= 0) return;
+   const dim3 grid((e1 + 255) / 256, (unsigned)std::min(e2, 4096), (unsigned)std::min(e3, 4096));
+   if (es == 16) box_copy_kernel<uint4><<<grid, 256, 0, ctx->stream>>>((uint4 *)dst, d1, d1 * d2, (const uint4 *)src, s1, s1 * s2, e1, e2, e3);
+   else if (es == 8) box_copy_kernel<uint2><<<grid, 256, 0, ctx->stream>>>((uint2 *)dst, d1, d1 * d2, (const uint2 *)src, s1, s1 * s2, e1, e2, e3);
+   else if (es == 4) box_copy_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>((uint32_t *)dst, d1, d1 * d2, (const uint32_t *)src, s1, s1 * s2, e1, e2, e3);
+   else D2D_REQUIRE(false, "box copy: unsupported element size");
+   D2D_CHECK_CUDA(cudaGetLastError());
+   ctx->launches++;
+}
 } // namespace d2d

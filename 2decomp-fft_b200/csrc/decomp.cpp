@@ -62,6 +62,14 @@ void decomp_init(Decomp &d, int nx, int ny, int nz, int p_row, int p_col, int ra
       d.y2disp[i] = i ? d.y2disp[i - 1] + d.y2cnts[i - 1] : 0;
       d.z2disp[i] = i ? d.z2disp[i - 1] + d.z2cnts[i - 1] : 0;
    }
+   // EVEN (src/decomp_2d.f90:1197-1203): pad every message to the size of the largest one -- the last blocks are the largest
+   d.x1count = (int64_t)d.x1dist[p_row - 1] * d.y1dist[p_row - 1] * d.xsz[2];
+   d.y1count = d.x1count;
+   d.y2count = (int64_t)d.y2dist[p_col - 1] * d.z2dist[p_col - 1] * d.zsz[0];
+   d.z2count = d.y2count;
+   for (int i = 0; i < p_row; i++) { d.e_cnts_row[i] = d.x1count; d.e_disp_row[i] = (int64_t)i * d.x1count; }
+   for (int i = 0; i < p_col; i++) { d.e_cnts_col[i] = d.y2count; d.e_disp_col[i] = (int64_t)i * d.y2count; }
+   d.even = (nx % p_row == 0 && ny % p_row == 0 && ny % p_col == 0 && nz % p_col == 0) ? 1 : 0; // :443-454
 }
 
 // best_2d_grid (src/decomp_2d_init_fin.f90:270-300) on top of findfactor (src/factor.f90:17-54)
@@ -86,8 +94,14 @@ struct Side {
    int np;
 };
 // the dist/disp table used by pencil `pencil` when talking to pencil `other`
-Side side_of(const Decomp &d, int pencil, int other)
+Side side_of(const Decomp &d, int pencil, int other, bool even = false)
 {
+   if (even) { // padded equal counts, segment m at m * count (mem_split_* / mem_merge_* under EVEN: pos = m * count + 1)
+      if (pencil == 0) return {d.x1dist, d.x1off, d.e_cnts_row, d.e_disp_row, d.p_row};
+      if (pencil == 2) return {d.z2dist, d.z2off, d.e_cnts_col, d.e_disp_col, d.p_col};
+      if (other == 0) return {d.y1dist, d.y1off, d.e_cnts_row, d.e_disp_row, d.p_row};
+      return {d.y2dist, d.y2off, d.e_cnts_col, d.e_disp_col, d.p_col};
+   }
    if (pencil == 0) return {d.x1dist, d.x1off, d.x1cnts, d.x1disp, d.p_row};
    if (pencil == 2) return {d.z2dist, d.z2off, d.z2cnts, d.z2disp, d.p_col};
    if (other == 0) return {d.y1dist, d.y1off, d.y1cnts, d.y1disp, d.p_row};
@@ -131,15 +145,15 @@ PieceMap natural_map(const Decomp &d, int pencil, void *ptr)
    return m;
 }
 
-PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es)
+PieceMap send_map(const Decomp &d, int from, int to, void *sendbuf, int es, bool even)
 {
-   return pieces(d, from, side_of(d, from, to), (char *)sendbuf, es);
+   return pieces(d, from, side_of(d, from, to, even), (char *)sendbuf, es);
 }
-PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es)
+PieceMap recv_map(const Decomp &d, int from, int to, void *recvbuf, void *sendbuf, int es, bool even)
 {
-   PieceMap m = pieces(d, to, side_of(d, to, from), (char *)recvbuf, es);
+   PieceMap m = pieces(d, to, side_of(d, to, from, even), (char *)recvbuf, es);
    // the block this rank "sends to itself" is never moved: read it where the producer wrote it
-   const Side s = side_of(d, from, to);
+   const Side s = side_of(d, from, to, even);
    const int me = (from == 0 || to == 0) ? d.c1 : d.c2;
    m.ptr[me] = (char *)sendbuf + (size_t)es * s.disp[me];
    return m;
@@ -317,14 +331,14 @@ void fft_exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendb
 
 // all-to-all(v) with the peers of the row / column communicator (self excluded).
 // Replaces decomp_2d_nccl_alltoall_{col,row}_* (src/decomp_2d_nccl.f90:214-473) / MPI_ALLTOALLV.
-void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w)
+void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, void *recvbuf, int es, int send_w, int recv_w, bool even)
 {
    const bool col = (from == 0 || to == 0);
    const int np = col ? d.p_row : d.p_col;
    const int me = col ? d.c1 : d.c2;
    if (np == 1) return;
    D2D_REQUIRE(ctx->tr != nullptr, "context has no transport but the process grid has more than one rank");
-   const Side s = side_of(d, from, to), r = side_of(d, to, from);
+   const Side s = side_of(d, from, to, even), r = side_of(d, to, from, even);
    const bool p2p = p2p_active(ctx);
    std::vector<PeerXfer> xf;
    std::vector<size_t> dst_off;
@@ -342,7 +356,7 @@ void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, 
       if (p2p) { // where the destination rank expects the block from this rank
          Decomp dm;
          decomp_init(dm, d.nx, d.ny, d.nz, d.p_row, d.p_col, x.peer);
-         const Side rm = side_of(dm, to, from);
+         const Side rm = side_of(dm, to, from, even);
          D2D_REQUIRE(rm.cnts[me] == s.cnts[m], "exchange: block sizes of the two sides disagree");
          dst_off.push_back((size_t)es * rm.disp[me]);
       }
@@ -357,13 +371,14 @@ void exchange(Ctx *ctx, const Decomp &d, int from, int to, const void *sendbuf, 
    }
 }
 
-size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es)
+size_t uniform_pencil_bytes(const Ctx *ctx, const Decomp &d, int es, bool even)
 {
    int64_t m = 0;
    for (int r = 0; r < ctx->nranks; r++) {
       Decomp a;
       decomp_init(a, d.nx, d.ny, d.nz, ctx->p_row, ctx->p_col, r);
       m = std::max(m, a.max_pencil());
+      if (even) m = std::max(m, std::max(a.x1count * a.p_row, a.y2count * a.p_col)); // src/decomp_2d.f90:443-446
    }
    return (size_t)es * (size_t)m;
 }

@@ -40,9 +40,26 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
    CopyArgs c{};
    // pack / receive buffers: the context's work buffers 0 and 1, sized for the largest pencil of ANY rank so that every rank
    // grows (and republishes to its peers) at the same call -- a rank-local size would leave the peers with stale mappings
-   ctx->ensure_buffers(2, uniform_pencil_bytes(ctx, d, es), false);
+   const bool even = ctx->even;
+   ctx->ensure_buffers(2, uniform_pencil_bytes(ctx, d, es, even), false);
    void *w1 = ctx->work[0], *w2 = ctx->work[1];
    const bool p2p = p2p_active(ctx);
+   if (even) {
+      // EVEN builds of the reference: every message padded to one count per communicator (MPI_ALLTOALL instead of
+      // MPI_ALLTOALLV, src/transpose_x_to_y.f90:99-110), segment m of both buffers at m * count; y<->z stage through the work
+      // buffers like x<->y (the Z-pencil is no longer the receive / send buffer itself).  Same pencils as the default layout.
+      ctx->wait_buffer_idle(0, ctx->stream);
+      c.in = natural_map(d, from, nsrc);
+      c.out = send_map(d, from, to, w1, es, true);
+      pencil_space(d, from, c);
+      launch_copy(ctx, c, es, "pack");
+      exchange(ctx, d, from, to, w1, w2, es, 0, 1, true);
+      c.in = recv_map(d, from, to, w2, w1, es, true);
+      c.out = natural_map(d, to, dst);
+      pencil_space(d, to, c);
+      launch_copy(ctx, c, es, "unpack");
+      return;
+   }
    switch (direction) {
    case D2D_X_TO_Y:
    case D2D_Y_TO_X: {
@@ -50,12 +67,12 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
       c.in = natural_map(d, from, nsrc);
       c.out = send_map(d, from, to, w1, es);
       pencil_space(d, from, c);
-      launch_copy(ctx, c, es);
+      launch_copy(ctx, c, es, "pack");
       exchange(ctx, d, from, to, w1, w2, es, 0, 1);
       c.in = recv_map(d, from, to, w2, w1, es);
       c.out = natural_map(d, to, dst);
       pencil_space(d, to, c);
-      launch_copy(ctx, c, es);
+      launch_copy(ctx, c, es, "unpack");
       break;
    }
    case D2D_Y_TO_Z: { // the receive buffer IS the Z pencil (transpose_y_to_z.f90:538)
@@ -64,7 +81,7 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
       c.out = send_map(d, 1, 2, w1, es);
       c.out.ptr[me] = (char *)dst + (size_t)es * d.z2disp[me]; // own block goes straight home
       pencil_space(d, 1, c);
-      launch_copy(ctx, c, es);
+      launch_copy(ctx, c, es, "pack");
       if (!p2p) {
          exchange(ctx, d, 1, 2, w1, dst, es, 0, -1);
       } else { // peers push into the mapped work buffer; the blocks (contiguous z-slabs) then move home
@@ -81,7 +98,7 @@ void transpose(Ctx *ctx, const Decomp &d, int direction, int es, const void *src
       c.in = recv_map(d, 2, 1, w2, nsrc, es);
       c.out = natural_map(d, 1, dst);
       pencil_space(d, 1, c);
-      launch_copy(ctx, c, es);
+      launch_copy(ctx, c, es, "unpack");
       break;
    }
    }

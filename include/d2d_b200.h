@@ -70,6 +70,11 @@ int d2d_ctx_create_in_group(d2d_ctx **ctx, d2d_group *grp, int rank, int p_row, 
 int d2d_ctx_destroy(d2d_ctx *ctx);
 int d2d_ctx_sync(d2d_ctx *ctx);                    /* cudaStreamSynchronize of the context's streams */
 int d2d_ctx_set_blocking(d2d_ctx *ctx, int blocking);
+/* EVEN builds of the reference (-DEVEN: padded MPI_ALLTOALL instead of MPI_ALLTOALLV, src/transpose_*.f90 `#ifdef EVEN`
+ * branches, counts from src/decomp_2d.f90:1186-1204): the bare transposes lay their send / receive buffers out with one
+ * padded count per communicator (segment m at m * count) and exchange equal-sized messages.  The pencils that come out are
+ * the same; what changes is the buffer footprint (src/decomp_2d.f90:443-446).  Default off, like the reference. */
+int d2d_ctx_set_even(d2d_ctx *ctx, int even);
 void *d2d_ctx_stream(d2d_ctx *ctx);                /* cudaStream_t */
 int d2d_ctx_info(const d2d_ctx *ctx, int *nranks, int *rank, int dims[2], int coord[2], int *transport);
 int64_t d2d_ctx_launch_count(const d2d_ctx *ctx);  /* kernels launched by this context so far */
@@ -95,6 +100,9 @@ int d2d_decomp_dist(const d2d_decomp *decomp, int *x1dist, int *y1dist, int *y2d
 int d2d_decomp_counts(const d2d_decomp *decomp, int64_t *x1cnts, int64_t *y1cnts, int64_t *y2cnts, int64_t *z2cnts,
                       int64_t *x1disp, int64_t *y1disp, int64_t *y2disp, int64_t *z2disp);
 
+/* x1count / y1count / y2count / z2count of an EVEN build (src/decomp_2d.f90:1197-1203) and decomp%even (:448-454) */
+int d2d_decomp_even(const d2d_decomp *decomp, int64_t *x1count, int64_t *y1count, int64_t *y2count, int64_t *z2count, int *even);
+
 /* ---- transposes --------------------------------------------------------------------------------
  * transpose_{x_to_y,y_to_z,z_to_y,y_to_x}_{real,complex} (src/transpose_*.f90 long variants):
  * pack -> all-to-all(v) -> unpack; dims==1 is a copy.  Bit-exact data movement. */
@@ -103,6 +111,16 @@ int d2d_transpose_x_to_y(d2d_ctx *ctx, const d2d_decomp *decomp, int dtype, int 
 int d2d_transpose_y_to_z(d2d_ctx *ctx, const d2d_decomp *decomp, int dtype, int is_complex, const void *src, void *dst);
 int d2d_transpose_z_to_y(d2d_ctx *ctx, const d2d_decomp *decomp, int dtype, int is_complex, const void *src, void *dst);
 int d2d_transpose_y_to_x(d2d_ctx *ctx, const d2d_decomp *decomp, int dtype, int is_complex, const void *src, void *dst);
+
+/* ---- halo cells ---------------------------------------------------------------------------------
+ * update_halo (src/halo.f90:101-198, src/halo_common.f90) + halo_exchange (src/halo.f90:311-399,
+ * src/halo_exchange_{x,y,z}_body.f90): `in` is a pencil of `decomp` (pencil = 0 X, 1 Y, 2 Z), `out` the same pencil with
+ * `level` ghost layers on both sides of its two decomposed axes -- X: (n1, n2+2L, n3+2L), Y: (n1+2L, n2, n3+2L),
+ * Z: (n1+2L, n2+2L, n3).  The interior is copied, then the ghost layers are filled from the neighbouring pencils in two
+ * exchanges (the second one carries the corners).  periodic[3] = periodic_bc of decomp_2d_init (NULL: none); ghost layers
+ * beyond a non-periodic boundary are left untouched.  Collective over the ranks of the context. */
+int d2d_halo_update(d2d_ctx *ctx, const d2d_decomp *decomp, int pencil, int level, int dtype, int is_complex, const int periodic[3],
+                    const void *in, void *out);
 
 /* ---- FFT ---------------------------------------------------------------------------------------
  * plan = decomp_2d_fft_engine_init + init_fft_engine (src/fft_common.f90:141-242,

@@ -131,6 +131,19 @@ void orc_decomp_init(int nx, int ny, int nz, int p_row, int p_col, int rank, orc
 
 int orc_sizeof_decomp(void) { return (int)sizeof(orc_decomp); }
 
+/* EVEN builds (src/decomp_2d.f90:1186-1204): the padded all-to-all counts -- "the last blocks along pencils always get
+ * assigned more mesh points" -- and decomp%even (:448-454).  out = {x1count, y1count, y2count, z2count}. */
+void orc_even_counts(int nx, int ny, int nz, int p_row, int p_col, int rank, int64_t out[4], int *even)
+{
+   orc_decomp d;
+   orc_decomp_init(nx, ny, nz, p_row, p_col, rank, &d);
+   out[0] = (int64_t)d.x1dist[p_row - 1] * d.y1dist[p_row - 1] * d.xsz[2];
+   out[1] = out[0];
+   out[2] = (int64_t)d.y2dist[p_col - 1] * d.z2dist[p_col - 1] * d.zsz[0];
+   out[3] = out[2];
+   *even = (nx % p_row == 0 && ny % p_row == 0 && ny % p_col == 0 && nz % p_col == 0);
+}
+
 /* One OpenMP thread plays one MPI rank of the simulated world.  Launchers such as torchrun export OMP_NUM_THREADS=1,
  * which would silently serialise the ranks: the harness sets the thread count explicitly and reads it back. */
 #ifdef _OPENMP

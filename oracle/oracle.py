@@ -78,6 +78,14 @@ def set_threads(n):
     return int(lib().orc_get_max_threads())
 
 
+def even_counts(nx, ny, nz, p_row, p_col, rank):
+    """(x1count, y1count, y2count, z2count), decomp%even of an EVEN build (src/decomp_2d.f90:1186-1204, :448-454)"""
+    out = (C.c_int64 * 4)()
+    ev = C.c_int()
+    lib().orc_even_counts(nx, ny, nz, p_row, p_col, rank, out, C.byref(ev))
+    return tuple(out), bool(ev.value)
+
+
 def best_2d_grid(nproc):
     r, c = C.c_int(), C.c_int()
     lib().orc_best_2d_grid(nproc, C.byref(r), C.byref(c))
@@ -243,3 +251,50 @@ def gather(parts, shape, grid, pencil):
         st, sz = d.st(pencil), d.sz(pencil)
         glob[st[0]:st[0] + sz[0], st[1]:st[1] + sz[1], st[2]:st[2] + sz[2]] = parts[r]
     return glob
+
+
+def update_halo_world(glob, grid, pencil, level, periodic=(False, False, False)):
+    """update_halo + halo_exchange of the reference on a simulated world (src/halo.f90:101-198, 311-399; src/halo_common.f90;
+    src/halo_exchange_{x,y,z}_body.f90), numpy restatement: per-rank pencils of `glob` (pencil = 0 X, 1 Y, 2 Z) with `level`
+    ghost layers on the two decomposed axes.  Two successive exchanges -- first the axis split by dims(1), then the axis
+    split by dims(2) -- whose strips span the FULL extent of the other axes, ghost layers included (MPI_TYPE_VECTOR counts
+    of the bodies), so the second one carries the corners.  Neighbours: MPI_CART_SHIFT of init_neighbour (src/halo.f90:55-99);
+    MPI_PROC_NULL sides stay untouched (0 here: the reference leaves them uninitialised)."""
+    p_row, p_col = grid
+    ins = scatter(glob, grid, pencil)
+    ax1 = 1 if pencil == 0 else 0
+    ax2 = 1 if pencil == 2 else 2
+    h = [0, 0, 0]
+    h[ax1] = h[ax2] = level
+    outs = []
+    for a in ins:
+        o = np.zeros(tuple(a.shape[i] + 2 * h[i] for i in range(3)), dtype=a.dtype, order="F")
+        o[h[0]:h[0] + a.shape[0], h[1]:h[1] + a.shape[1], h[2]:h[2] + a.shape[2]] = a
+        outs.append(o)
+    if level == 0:
+        return outs
+    for ax, npd in ((ax1, p_row), (ax2, p_col)):
+        per = bool(periodic[ax])
+        new = [o.copy(order="F") for o in outs]
+        for r in range(p_row * p_col):
+            c1, c2 = r // p_col, r % p_col
+            me = c1 if ax == ax1 else c2
+            im = me - 1 if me > 0 else (npd - 1 if per else None)
+            ip = me + 1 if me < npd - 1 else (0 if per else None)
+
+            def rank_of(i):
+                return i * p_col + c2 if ax == ax1 else c1 * p_col + i
+
+            def sl(lo, hi):
+                s = [slice(None)] * 3
+                s[ax] = slice(lo, hi)
+                return tuple(s)
+            n = outs[r].shape[ax]
+            if im is not None:  # receive from minus: that neighbour's to-plus strip (its last `level` interior layers)
+                src = outs[rank_of(im)]
+                new[r][sl(0, level)] = src[sl(src.shape[ax] - 2 * level, src.shape[ax] - level)]
+            if ip is not None:  # receive from plus: that neighbour's to-minus strip (its first `level` interior layers)
+                src = outs[rank_of(ip)]
+                new[r][sl(n - level, n)] = src[sl(level, 2 * level)]
+        outs = new
+    return outs

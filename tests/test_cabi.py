@@ -66,3 +66,30 @@ def test_invalid_grid_reports_reference_error():
     with pytest.raises(p.Decomp2dError) as e:
         p.DecompInfo.for_rank(4, 4, 4, 8, 1, 0)
     assert "p_row" in str(e.value)
+
+
+@pytest.mark.parametrize("shape,grid", [((17, 13, 11), (2, 2)), ((1024, 1024, 513), (2, 4)), ((64, 64, 64), (2, 4)), ((34, 26, 22), (4, 2))])
+def test_even_counts_match_oracle_and_formula(shape, grid):
+    """x1count ... z2count of the reference's EVEN builds (src/decomp_2d.f90:1197-1203: the LAST blocks are the largest) and
+    decomp%even (:448-454), against the oracle restatement and the formula evaluated with numpy"""
+    import numpy as np
+    import oracle as orc
+    p = pkg()
+    nx, ny, nz = shape
+    pr, pc = grid
+
+    def dist(n, k):
+        return np.array([n // k + (1 if i >= k - n % k else 0) for i in range(k)])
+    for rank in range(pr * pc):
+        d = p.DecompInfo.for_rank(nx, ny, nz, pr, pc, rank)
+        want, ev = orc.even_counts(nx, ny, nz, pr, pc, rank)
+        assert (d.x1count, d.y1count, d.y2count, d.z2count) == want and d.even == ev
+        c2 = rank % pc
+        c1 = rank // pc
+        x1 = dist(nx, pr)[-1] * dist(ny, pr)[-1] * dist(nz, pc)[c2]
+        y2 = dist(ny, pc)[-1] * dist(nz, pc)[-1] * dist(nx, pr)[c1]
+        assert want == (x1, x1, y2, y2)
+        assert ev == (nx % pr == 0 and ny % pr == 0 and ny % pc == 0 and nz % pc == 0)
+        # a padded buffer holds every real block
+        assert max(d.x1cnts) <= d.x1count and max(d.y1cnts) <= d.y1count and max(d.y2cnts) <= d.y2count and max(d.z2cnts) <= d.z2count
+        d.finalize()

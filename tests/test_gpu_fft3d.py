@@ -65,6 +65,39 @@ def test_test2d_transposes_bit_exact(shape, grid, dtype):
     assert all(run_ranks(grid[0] * grid[1], body))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64])
+@pytest.mark.parametrize("grid", [(1, 2), (2, 2), (2, 4), (4, 2)])
+@pytest.mark.parametrize("shape", [(17, 13, 11), (34, 26, 22), (32, 16, 64)])
+def test_test2d_transposes_even_layout(shape, grid, dtype):
+    """the same four transposes through the padded equal-count buffers of the reference's EVEN builds (d2d_ctx_set_even):
+    ragged grids pad, the pencils are bit-identical"""
+    import torch
+    p = pkg()
+    g = _index_field(shape, dtype)
+    want = [orc.scatter(g, grid, pen) for pen in range(3)]
+    tdt = {np.float64: torch.float64, np.complex64: torch.complex64}[dtype]
+
+    def body(rank, group):
+        d2d = p.Decomp2d(*shape, grid[0], grid[1], rank=rank, nranks=grid[0] * grid[1], group=group, device=0)
+        d2d.set_even(True)
+        u1, u2, u3 = d2d.alloc_x(tdt), d2d.alloc_y(tdt), d2d.alloc_z(tdt)
+        u1.copy_(torch.from_numpy(want[0][rank]))
+        d2d.transpose_x_to_y(u1, u2)
+        assert np.array_equal(u2.cpu().numpy(), want[1][rank]), "x->y"
+        d2d.transpose_y_to_z(u2, u3)
+        assert np.array_equal(u3.cpu().numpy(), want[2][rank]), "y->z"
+        u2.zero_()
+        d2d.transpose_z_to_y(u3, u2)
+        assert np.array_equal(u2.cpu().numpy(), want[1][rank]), "z->y"
+        u1.zero_()
+        d2d.transpose_y_to_x(u2, u1)
+        assert np.array_equal(u1.cpu().numpy(), want[0][rank]), "y->x"
+        d2d.finalize()
+        return True
+
+    assert all(run_ranks(grid[0] * grid[1], body))
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("fmt", [orc.PHYSICAL_IN_X, orc.PHYSICAL_IN_Z])
 @pytest.mark.parametrize("grid", GRIDS)

@@ -179,3 +179,29 @@ def test_c2r_uses_imag_of_dc_and_nyquist_like_reference():
     a2[n // 2].imag = 0
     ref = np.fft.irfft(a2, n=n, axis=0) * n
     assert np.max(np.abs(got - ref)) < 1e-12
+
+
+@pytest.mark.parametrize("pencil", [0, 1, 2])
+@pytest.mark.parametrize("grid", [(1, 1), (2, 2), (2, 3)])
+def test_halo_oracle_periodic_closed_form(pencil, grid):
+    """with every axis periodic each ghost cell of update_halo is the global field at the wrapped index (the property
+    examples/halo_test relies on); without periodicity the ghost layers beyond the domain stay untouched"""
+    shape, level = (7, 6, 9), 2
+    g = np.arange(1, np.prod(shape) + 1, dtype=np.float64).reshape(shape, order="F")
+    outs = orc.update_halo_world(g, grid, pencil, level, (True, True, True))
+    axes = [a for a in range(3) if a != pencil]
+    for r, o in enumerate(outs):
+        d = orc.Decomp(*shape, grid[0], grid[1], r)
+        st = d.st(pencil)
+        idx = [np.arange(o.shape[a]) + st[a] - (level if a in axes else 0) for a in range(3)]
+        want = g[np.ix_(idx[0] % shape[0], idx[1] % shape[1], idx[2] % shape[2])]
+        assert np.array_equal(o, want), (pencil, grid, r)
+    outs = orc.update_halo_world(g, grid, pencil, level)
+    for r, o in enumerate(outs):
+        d = orc.Decomp(*shape, grid[0], grid[1], r)
+        st = d.st(pencil)
+        idx = [np.arange(o.shape[a]) + st[a] - (level if a in axes else 0) for a in range(3)]
+        inside = np.ix_(*[(i >= 0) & (i < shape[a]) for a, i in enumerate(idx)])
+        want = np.zeros_like(o)
+        want[inside] = g[np.ix_(*[i[(i >= 0) & (i < shape[a])] for a, i in enumerate(idx)])]
+        assert np.array_equal(o, want), (pencil, grid, r)

@@ -84,6 +84,14 @@ def main():
                 d2d.transpose_z_to_y(u3, u2)
                 d2d.transpose_y_to_x(u2, u1)
                 t_ok = t_ok and np.array_equal(u2.cpu().numpy(), want[1][rank]) and np.array_equal(u1.cpu().numpy(), want[0][rank])
+                # halo exchange over the same transport (periodic in x and z), bit-exact
+                for pen in range(3):
+                    hw = orc.update_halo_world(idx, grid, pen, 2, (True, False, True))
+                    hin = (d2d.alloc_x, d2d.alloc_y, d2d.alloc_z)[pen](torch.float64)
+                    hin.copy_(torch.from_numpy(want[pen][rank]))
+                    d2d.periodic_bc = (True, False, True)
+                    hout = d2d.update_halo(hin, 2, opt_pencil=pen + 1)
+                    t_ok = t_ok and np.array_equal(hout.cpu().numpy(), hw[rank])
                 err = max(e1, e2, e3)
                 worst = max(worst, err)
                 bad = (err > 1e-12) or not t_ok
