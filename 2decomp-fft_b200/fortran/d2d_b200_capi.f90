@@ -34,6 +34,65 @@ module d2d_b200_capi
          integer(c_int) :: ierr
       end function d2d_ctx_create
 
+      ! the same without NCCL: the library all-gathers its CUDA-IPC handles through a callback (MPI_Allgather on
+      ! decomp_2d_comm, see d2d_b200_allgather in decomp_2d_b200.f90); the data plane is its own peer-memory exchange
+      function d2d_ctx_create_bootstrap(ctx, nranks, rank, p_row, p_col, device, allgather, user) &
+         bind(C, name="d2d_ctx_create_bootstrap") result(ierr)
+         import :: c_int, c_ptr, c_funptr
+         type(c_ptr), intent(out) :: ctx
+         integer(c_int), value :: nranks, rank, p_row, p_col, device
+         type(c_funptr), value :: allgather   ! int (*)(void *user, const void *send, void *recv, int64_t bytes)
+         type(c_ptr), value :: user
+         integer(c_int) :: ierr
+      end function d2d_ctx_create_bootstrap
+
+      ! EVEN builds (padded MPI_ALLTOALL, src/decomp_2d.f90:1186-1204): same pencils, padded buffer layout
+      function d2d_ctx_set_even(ctx, even) bind(C, name="d2d_ctx_set_even") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: even
+         integer(c_int) :: ierr
+      end function d2d_ctx_set_even
+
+      function d2d_decomp_even(decomp, x1count, y1count, y2count, z2count, even) bind(C, name="d2d_decomp_even") result(ierr)
+         import :: c_int, c_ptr, c_int64_t
+         type(c_ptr), value :: decomp
+         integer(c_int64_t), intent(out) :: x1count, y1count, y2count, z2count
+         integer(c_int), intent(out) :: even
+         integer(c_int) :: ierr
+      end function d2d_decomp_even
+
+      ! update_halo + halo_exchange (src/halo.f90:101-198, 311-399): `out` is the pencil with `level` ghost layers
+      function d2d_halo_update(ctx, decomp, pencil, level, dtype, is_complex, periodic, in, out) &
+         bind(C, name="d2d_halo_update") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx, decomp
+         integer(c_int), value :: pencil, level, dtype, is_complex
+         integer(c_int), intent(in) :: periodic(3)
+         type(c_ptr), value :: in, out
+         integer(c_int) :: ierr
+      end function d2d_halo_update
+
+      ! decomp_2d_fft_3d on HOST arrays (upload, transform, download pipelined inside the library)
+      function d2d_fft_3d_r2c_host(plan, in_r, out_c) bind(C, name="d2d_fft_3d_r2c_host") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: plan, in_r, out_c
+         integer(c_int) :: ierr
+      end function d2d_fft_3d_r2c_host
+
+      function d2d_fft_3d_c2r_host(plan, in_c, out_r) bind(C, name="d2d_fft_3d_c2r_host") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: plan, in_c, out_r
+         integer(c_int) :: ierr
+      end function d2d_fft_3d_c2r_host
+
+      function d2d_fft_3d_c2c_host(plan, in, out, isign) bind(C, name="d2d_fft_3d_c2c_host") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: plan, in, out
+         integer(c_int), value :: isign
+         integer(c_int) :: ierr
+      end function d2d_fft_3d_c2c_host
+
       function d2d_ctx_destroy(ctx) bind(C, name="d2d_ctx_destroy") result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: ctx

@@ -31,6 +31,48 @@ contains
                                     int(p_col, c_int), int(device, c_int)), __FILE__, __LINE__)
    end subroutine d2d_b200_init
 
+   ! NCCL-free variant: the library only needs an all-gather of a few hundred bytes per rank at context / plan creation
+   ! (its CUDA-IPC handles); MPI_Allgather on decomp_2d_comm provides it -- the reference bootstraps NCCL through MPI the
+   ! same way (src/decomp_2d_nccl.f90:181-191).  Build with -DD2D_BOOTSTRAP_MPI to select it.
+   function d2d_b200_allgather(user, send, recv, nbytes) bind(C) result(ierr)
+      type(c_ptr), value :: user, send, recv
+      integer(c_int64_t), value :: nbytes
+      integer(c_int) :: ierr
+      integer(c_signed_char), pointer :: s(:), r(:)
+      integer :: code
+      call c_f_pointer(send, s, [nbytes])
+      call c_f_pointer(recv, r, [nbytes * nproc])
+      call MPI_ALLGATHER(s, int(nbytes), MPI_BYTE, r, int(nbytes), MPI_BYTE, decomp_2d_comm, code)
+      ierr = int(code, c_int)
+   end function d2d_b200_allgather
+
+   subroutine d2d_b200_init_mpi(p_row, p_col, device)
+      integer, intent(in) :: p_row, p_col, device
+      call d2d_check(d2d_ctx_create_bootstrap(d2d_ctx, int(nproc, c_int), int(nrank, c_int), int(p_row, c_int), &
+                                              int(p_col, c_int), int(device, c_int), c_funloc(d2d_b200_allgather), c_null_ptr), &
+                     __FILE__, __LINE__)
+#ifdef EVEN
+      call d2d_check(d2d_ctx_set_even(d2d_ctx, 1_c_int), __FILE__, __LINE__)
+#endif
+   end subroutine d2d_b200_init_mpi
+
+   ! replaces the body of halo_exchange_{real,complex} (src/halo.f90:311-399) on the device: `out` was allocated by
+   ! update_halo with the halo extents (src/halo_common.f90:19-23); periodic_x/y/z are the module variables of decomp_2d_mpi
+   subroutine d2d_b200_update_halo(handle, ipencil, level, is_complex, in, out)
+      type(c_ptr), intent(in) :: handle, in, out
+      integer, intent(in) :: ipencil, level
+      logical, intent(in) :: is_complex
+      integer(c_int) :: dtype, per(3)
+#ifdef DOUBLE_PREC
+      dtype = D2D_F64
+#else
+      dtype = D2D_F32
+#endif
+      per = [merge(1_c_int, 0_c_int, periodic_x), merge(1_c_int, 0_c_int, periodic_y), merge(1_c_int, 0_c_int, periodic_z)]
+      call d2d_check(d2d_halo_update(d2d_ctx, handle, int(ipencil - 1, c_int), int(level, c_int), dtype, &
+                                     merge(1_c_int, 0_c_int, is_complex), per, in, out), __FILE__, __LINE__)
+   end subroutine d2d_b200_update_halo
+
    subroutine d2d_b200_fin()
       if (c_associated(d2d_ctx)) call d2d_check(d2d_ctx_destroy(d2d_ctx), __FILE__, __LINE__)
       d2d_ctx = c_null_ptr
