@@ -113,6 +113,8 @@ struct Ctx {
    // grow-only work buffers (the reference's work1/work2 high-water mark, src/decomp_2d.f90:461-485)
    void *work[kCtxBuffers] = {nullptr, nullptr, nullptr, nullptr};
    size_t work_bytes[kCtxBuffers] = {0, 0, 0, 0};
+   void *scratch = nullptr; // global-memory scratch of the two-kernel transforms of very long lines (fft_any.cu)
+   size_t scratch_bytes = 0;
    struct P2P *p2p = nullptr; // peer-mapped work buffers + flags (p2p.cpp); null when unused
    // chunk-wise pipelined chains (fft_plan.cpp run_chain_pipe): the exchanges run on their own streams -- one per peer
    // of a communicator for the copy-engine pushes of the peer-memory path, comm_stream for the transports' exchanges

@@ -252,6 +252,7 @@ Ctx::~Ctx()
    for (auto e : event_pool) cudaEventDestroy(e);
    for (int i = 0; i < kCtxBuffers; i++)
       if (work[i]) cudaFree(work[i]);
+   if (scratch) cudaFree(scratch);
    if (stream) cudaStreamDestroy(stream);
 }
 

@@ -139,24 +139,21 @@ void fft_any_release_all()
 // largest transform length the shared-memory kernel takes (one line per block, two buffers + the root table)
 int fft_any_max_n(int f64) { return (int)(kAnySmemBudget / (3 * (size_t)(f64 ? 16 : 8))) - 1; }
 
-cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
+// geometry of one launch: lines per block (a power of two), shared-memory pitch, which axis the lanes follow on each side
+static size_t configure_any(FftArgsAny &ga, int f64, int mode, bool split_step)
 {
+   const FftArgs &g = ga.a;
    const int n = g.n;
    const size_t ces = f64 ? 16 : 8;
-   D2D_REQUIRE(n >= 1 && n <= fft_any_max_n(f64),
-               "transform length " + std::to_string(n) + " is not supported (neither a compiled power of two nor <= " +
-                  std::to_string(fft_any_max_n(f64)) + ")");
-   FftArgsAny ga{};
-   ga.a = g;
-   ga.a.tw = roots_for(ctx->device, n, f64);
    ga.npass = fft_any_factorize(n, ga.radix, kMaxAnyPass);
    D2D_REQUIRE(ga.npass <= kMaxAnyPass, "too many factors");
    ga.pitch = n | 1;
-   // which axis is unit-stride on each side
-   if (mode == MODE_R2C) ga.in_fast_a = (g.rsa == 1 && g.rse != 1);
-   else ga.in_fast_a = (g.in.sa[0] == 1 && g.in.se[0] != 1);
-   if (mode == MODE_C2R) ga.out_fast_a = (g.rsa == 1 && g.rse != 1);
-   else ga.out_fast_a = (g.out.sa[0] == 1 && g.out.se[0] != 1);
+   if (!split_step) { // which axis is unit-stride on each side
+      if (mode == MODE_R2C) ga.in_fast_a = (g.rsa == 1 && g.rse != 1);
+      else ga.in_fast_a = (g.in.sa[0] == 1 && g.in.se[0] != 1);
+      if (mode == MODE_C2R) ga.out_fast_a = (g.rsa == 1 && g.rse != 1);
+      else ga.out_fast_a = (g.out.sa[0] == 1 && g.out.se[0] != 1);
+   }
    // lines per block (a power of two): 128-byte rows when lines are strided, about 2048 elements of work per block,
    // within the shared-memory budget; narrower (never below the row width) when that lets two blocks share an SM
    auto smem_of = [&](int lines) { return ces * ((size_t)n + 2 * (size_t)lines * ga.pitch); };
@@ -172,7 +169,86 @@ cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
    const int min_rows_log2 = pow2_ceil((long long)(64 / ces));
    while (ll > min_rows_log2 && smem_of(1 << ll) > 110 * 1024) ll--;
    ga.lines_log2 = ll;
-   const size_t smem = smem_of(1 << ll);
+   return smem_of(1 << ll);
+}
+
+// Lengths beyond the shared-memory kernel (n > fft_any_max_n): n = n1 n2 with both factors within its reach, as TWO launches of
+// the same kernel through a scratch array in global memory (the classic four-step split; the reference's generic backend takes
+// any length, src/glassman.f90:29-67):
+//   step A  for every i2 < n2: the n1-point transform over i1 of x[i1 n2 + i2], times exp(-2 pi i i2 k1 / n)  -> scratch[k1 n2 + i2]
+//   step B  for every k1 < n1: the n2-point transform over i2 of scratch[k1 n2 + i2]                          -> X[k1 + n1 k2]
+// Real transforms run as complex ones with the conversions of the reference's generic backend at the two ends (zero imaginary
+// part in, bins 0 .. n/2 out, src/fft_generic.f90:236-244; Hermitian completion in, real part out, :320-337).  A prime length
+// above the limit still has no kernel.
+static cudaError_t fft_any_launch_split(Ctx *ctx, const FftArgs &g, int f64, int mode)
+{
+   const int n = g.n, lim = fft_any_max_n(f64);
+   int n1 = 0;
+   for (int d = 2; (long long)d * d <= n; d++)
+      if (n % d == 0 && n / d <= lim) { n1 = d; if (d <= lim) break; }
+   D2D_REQUIRE(n1 >= 2 && n1 <= lim && n / n1 <= lim, "transform length " + std::to_string(n) + " is not supported (a factor above " +
+                                                         std::to_string(lim) + " has no kernel)");
+   const int n2 = n / n1;
+   const size_t ces = f64 ? 16 : 8;
+   const long long lines_a = (mode == MODE_C2C) ? g.na : g.na_real; // real transforms: one complex line per real line
+   const long long lines = lines_a * g.nb;
+   D2D_REQUIRE(lines_a * std::max(n1, n2) < (1LL << 31), "too many lines for the two-kernel transform");
+   const size_t need = (size_t)lines * (size_t)n * ces;
+   if (need > ctx->scratch_bytes) {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->scratch) D2D_CHECK_CUDA(cudaFree(ctx->scratch));
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&ctx->scratch, need));
+      ctx->scratch_bytes = need;
+   }
+   PieceMap sm{};
+   sm.np = 1;
+   sm.e0[0] = 0; sm.e0[1] = n;
+   sm.ptr[0] = ctx->scratch;
+   sm.se[0] = 1; sm.sa[0] = n; sm.sb[0] = (long long)n * lines_a;
+   const void *big = roots_for(ctx->device, n, f64);
+   cudaError_t e = cudaSuccess;
+   for (int step = 0; step < 2 && e == cudaSuccess; step++) {
+      FftArgsAny ga{};
+      ga.a = g;
+      ga.a.n = step == 0 ? n1 : n2;
+      ga.a.tw = roots_for(ctx->device, ga.a.n, f64);
+      ga.split = step == 0 ? n2 : n1;
+      ga.a.na = (int)(lines_a * ga.split);
+      ga.a.na_real = 0;
+      ga.n_full = n;
+      ga.big_tw = big;
+      if (step == 0) {
+         ga.a.out = sm;
+         ga.in_mul = n2; ga.in_add = 1; ga.out_mul = n2; ga.out_add = 1;
+         ga.tw_n = g.passthrough ? 0 : n;
+         ga.real_in = mode == MODE_R2C;
+         ga.herm_in = mode == MODE_C2R;
+         ga.in_fast_a = 1; ga.out_fast_a = 1; // consecutive sub-indices are consecutive elements on both sides
+      } else {
+         ga.a.in = sm;
+         ga.in_mul = 1; ga.in_add = n2;
+         ga.out_mul = g.passthrough ? 1 : n1; ga.out_add = g.passthrough ? n2 : 1;
+         ga.half_out = mode == MODE_R2C;
+         ga.real_out = mode == MODE_C2R;
+         ga.in_fast_a = 0; ga.out_fast_a = g.passthrough ? 0 : 1;
+      }
+      const size_t smem = configure_any(ga, f64, MODE_C2C, true);
+      e = f64 ? launch_any<double, MODE_C2C>(ga, smem, ctx->stream) : launch_any<float, MODE_C2C>(ga, smem, ctx->stream);
+   }
+   return e;
+}
+
+cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
+{
+   const int n = g.n;
+   D2D_REQUIRE(n >= 1, "transform length must be positive");
+   if (n > fft_any_max_n(f64)) return fft_any_launch_split(ctx, g, f64, mode);
+   FftArgsAny ga{};
+   ga.a = g;
+   ga.a.tw = roots_for(ctx->device, n, f64);
+   const size_t smem = configure_any(ga, f64, mode, false);
    if (mode == MODE_C2C) return f64 ? launch_any<double, MODE_C2C>(ga, smem, ctx->stream) : launch_any<float, MODE_C2C>(ga, smem, ctx->stream);
    if (mode == MODE_R2C) return f64 ? launch_any<double, MODE_R2C>(ga, smem, ctx->stream) : launch_any<float, MODE_R2C>(ga, smem, ctx->stream);
    return f64 ? launch_any<double, MODE_C2R>(ga, smem, ctx->stream) : launch_any<float, MODE_C2R>(ga, smem, ctx->stream);

@@ -41,6 +41,16 @@ struct FftArgsAny {
    int lines_log2;            // complex lines per block = 1 << lines_log2
    int pitch;                 // shared-memory pitch of a line, in complex elements (odd)
    int in_fast_a, out_fast_a; // 1: adjacent lines (axis a) are contiguous in global memory on that side
+   // ---- one step of a two-kernel transform of a length that does not fit in shared memory (n_full = n1 n2, fft_any.cu) ----
+   // split > 1 (C2C kernels only): the batch axis a is virtual, a' = a * split + sub; the element index on either side is
+   // e * mul + sub * add; a result element k is multiplied by exp(-2 pi i sub k / tw_n) when tw_n > 0 (table big_tw).
+   int split, in_mul, in_add, out_mul, out_add, tw_n, n_full;
+   const void *big_tw;
+   // conversions at the two ends of a real transform done as a complex one (src/fft_generic.f90:236-244, 320-337):
+   int real_in;  // read the REAL array (rptr / rse / rsa / rsb), imaginary part 0
+   int herm_in;  // the input holds bins 0 .. n_full/2: element e > n_full/2 is conj(bin n_full - e)
+   int half_out; // store bins 0 .. n_full/2 only
+   int real_out; // store the real part into the REAL array
 };
 
 // floor(x / d) for 0 <= x < 2^22, d >= 1, rd = 1.0f / d: (x + 0.5) / d is at least 0.5 / d away from an integer, far
@@ -174,6 +184,8 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
    T2 *buf0 = W + n;
    T2 *buf1 = buf0 + (size_t)L * pitch;
    __shared__ int line_a[kAnyMaxLines], line_b[kAnyMaxLines]; // (a, b) of the block's lines; a = -1: beyond the batch
+   __shared__ int line_sub[kAnyMaxLines];                     // split steps: the sub-index of the virtual batch index
+   const int split = (MODE == MODE_C2C && ga.split > 1) ? ga.split : 1;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = kAnyThreads / 32;
    // pass identity: TL threads per line
@@ -193,13 +205,18 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
       __syncthreads(); // W is staged; the previous group's stores have read the buffers and the line table
       if (tid < L) {
          const long long id = (grp << LL) + tid;
-         int a = -1, b = 0;
+         int a = -1, b = 0, sub = 0;
          if (id < total) {
             b = (int)(id / g.na);
             a = (int)(id - (long long)b * g.na);
+            if (split > 1) {
+               sub = a % split;
+               a /= split;
+            }
          }
          line_a[tid] = a;
          line_b[tid] = b;
+         line_sub[tid] = sub;
       }
       __syncthreads();
       // ------------------------------------------------------------------ load -> buf0
@@ -214,15 +231,36 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
          }
       };
       if constexpr (MODE == MODE_C2C) {
-         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
-            const int a = line_a[l];
-            T2 x = T2{0, 0};
-            if (a >= 0) {
-               x = load_piece<T2>(g.in, e, a, line_b[l]);
-               if (bw) x.y = -x.y;
-            }
-            buf0[l * pitch + e] = x;
-         });
+         if (split > 1) { // a step of a two-kernel transform
+            for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+               const int a = line_a[l];
+               T2 x = T2{0, 0};
+               if (a >= 0) {
+                  const int ea = e * ga.in_mul + line_sub[l] * ga.in_add;
+                  if (ga.real_in) {
+                     x.x = reinterpret_cast<const T *>(g.rptr)[(long long)ea * g.rse + (long long)a * g.rsa + (long long)line_b[l] * g.rsb];
+                  } else if (ga.herm_in && 2 * ea > ga.n_full) {
+                     x = load_piece<T2>(g.in, ga.n_full - ea, a, line_b[l]);
+                     x.y = -x.y;
+                  } else {
+                     x = load_piece<T2>(g.in, ea, a, line_b[l]);
+                     if (ga.herm_in && (ea == 0 || 2 * ea == ga.n_full)) x.y = 0; // like the other c2r kernels (and cuFFT)
+                  }
+                  if (bw) x.y = -x.y;
+               }
+               buf0[l * pitch + e] = x;
+            });
+         } else {
+            for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+               const int a = line_a[l];
+               T2 x = T2{0, 0};
+               if (a >= 0) {
+                  x = load_piece<T2>(g.in, e, a, line_b[l]);
+                  if (bw) x.y = -x.y;
+               }
+               buf0[l * pitch + e] = x;
+            });
+         }
       } else if constexpr (MODE == MODE_R2C) {
          const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
          for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
@@ -298,14 +336,33 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
       // ------------------------------------------------------------------ store
       if (g.debug & 1) continue;
       if constexpr (MODE == MODE_C2C) {
-         for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
-            const int a = line_a[l];
-            if (a >= 0) {
-               T2 x = res[l * pitch + e];
-               if (bw) x.y = -x.y;
-               store_piece<T2>(g.out, e, a, line_b[l], x);
-            }
-         });
+         if (split > 1) {
+            const T2 *__restrict__ bt = reinterpret_cast<const T2 *>(ga.big_tw);
+            for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
+               const int a = line_a[l];
+               if (a >= 0) {
+                  T2 x = res[l * pitch + e];
+                  const int sub = line_sub[l];
+                  if (ga.tw_n > 0) x = cmul(x, ldg_nc(bt + (long long)sub * e)); // sub * e < tw_n
+                  if (bw) x.y = -x.y;
+                  const int eo = e * ga.out_mul + sub * ga.out_add;
+                  if (ga.real_out) {
+                     reinterpret_cast<T *>(g.rptr)[(long long)eo * g.rse + (long long)a * g.rsa + (long long)line_b[l] * g.rsb] = x.x;
+                  } else if (!ga.half_out || 2 * eo <= ga.n_full) {
+                     store_piece<T2>(g.out, eo, a, line_b[l], x);
+                  }
+               }
+            });
+         } else {
+            for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
+               const int a = line_a[l];
+               if (a >= 0) {
+                  T2 x = res[l * pitch + e];
+                  if (bw) x.y = -x.y;
+                  store_piece<T2>(g.out, e, a, line_b[l], x);
+               }
+            });
+         }
       } else if constexpr (MODE == MODE_C2R) {
          T *__restrict__ rp = reinterpret_cast<T *>(g.rptr);
          for_each(n, ga.out_fast_a != 0, [&](int l, int e) {

@@ -104,7 +104,49 @@ def test_fp32_distance_to_fp32_oracle_is_reported():
 
 def test_unsupported_length_is_an_error_not_a_fallback():
     p, d2d, torch = _ctx()
-    t = _falloc(torch, (3 * 5 * 7 * 11 * 13, 2, 2), torch.complex128)  # beyond the any-length kernel's shared-memory limit
+    t = _falloc(torch, (4271, 2, 2), torch.complex128)  # a PRIME beyond the shared-memory kernel: no split into two kernels exists
     with pytest.raises(p.Decomp2dError, match="not supported"):
         d2d.c2c_1m(t, 0, -1)
+    d2d.finalize()
+
+
+@pytest.mark.parametrize("n,prec", [(4800, "f64"), (15015, "f64"), (16384, "f64"), (6000, "f64"), (10000, "f32")])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_long_lines_two_kernel_split(n, prec, axis):
+    """lengths beyond the shared-memory kernel (fp64: 4265, fp32: 8532) run as two launches through a scratch array
+    (n = n1 n2, four-step split): c2c both directions, r2c and c2r.  Pinned against the exact DFT (numpy's pocketfft): the
+    oracle -- like the reference's generic backend, src/glassman.f90:29-67 -- takes any length, but its recurrence twiddles
+    drift to ~5e-12 at n = 15015, so it is only required to agree to 1e-10."""
+    p, d2d, torch = _ctx()
+    cdt, rdt = (np.complex128, np.float64) if prec == "f64" else (np.complex64, np.float32)
+    tcd, trd = (torch.complex128, torch.float64) if prec == "f64" else (torch.complex64, torch.float32)
+    tol = 1e-12 if prec == "f64" else 1e-5
+    shape = [3, 4, 2]
+    shape[axis] = n
+    shape = tuple(shape)
+    rng = np.random.default_rng(n)
+    a = np.asfortranarray(rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(cdt)
+    t = _falloc(torch, shape, tcd)
+    out = _falloc(torch, shape, tcd)
+    for isign in (-1, 1):
+        t.copy_(torch.from_numpy(a))
+        d2d.c2c_1m(t, axis, isign, out=out)
+        ref = orc.c2c_1m(a.astype(np.complex128), axis, isign)
+        exact = np.fft.fft(a.astype(np.complex128), axis=axis) if isign == -1 else np.fft.ifft(a.astype(np.complex128), axis=axis) * n
+        assert _relerr(out.cpu().numpy(), exact) < tol, (n, axis, isign)
+        assert _relerr(out.cpu().numpy(), ref) < max(tol, 1e-10), (n, axis, isign)
+    if axis != 1:
+        r = np.asfortranarray(rng.uniform(-1, 1, shape)).astype(rdt)
+        cs = list(shape)
+        cs[axis] = n // 2 + 1
+        tr, tc = _falloc(torch, shape, trd), _falloc(torch, tuple(cs), tcd)
+        tr.copy_(torch.from_numpy(r))
+        d2d.r2c_1m(tr, tc, axis)
+        spec = np.fft.rfft(r.astype(np.float64), axis=axis)
+        assert _relerr(tc.cpu().numpy(), spec) < tol, (n, axis, "r2c")
+        assert _relerr(tc.cpu().numpy(), orc.r2c_1m(r.astype(np.float64), axis)) < max(tol, 1e-10), (n, axis, "r2c vs oracle")
+        back = _falloc(torch, shape, trd)
+        tc.copy_(torch.from_numpy(spec.astype(cdt)))
+        d2d.c2r_1m(tc, back, axis)
+        assert _relerr(back.cpu().numpy(), np.fft.irfft(spec, n=n, axis=axis) * n) < tol, (n, axis, "c2r")
     d2d.finalize()
