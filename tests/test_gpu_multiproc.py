@@ -26,15 +26,18 @@ def test_torchrun_parity(p2p):
     assert "failures 0" in r.stdout
 
 
-@pytest.mark.parametrize("world,chunks", [(2, "4"), (4, "3"), (2, "1")])
-def test_torchrun_parity_shared_gpu(world, chunks):
+@pytest.mark.parametrize("world,chunks,exchange", [(2, "4", "auto"), (4, "3", "auto"), (2, "1", "pipe"), (4, "4", "fused"), (8, "4", "auto")])
+def test_torchrun_parity_shared_gpu(world, chunks, exchange):
     """The default multi-rank data plane -- chunk-pipelined chains and transposes whose blocks are pushed by the copy engines
     into the peers' CUDA-IPC mapped buffers, ordered by stream memory operations -- with `world` processes SHARING GPU 0
     (bootstrap over gloo, no NCCL).  Runs on a single-GPU box: forward spectra, round trips and bit-exact transposes of
     every rank are compared with the oracle by tools/mgpu_check.py."""
-    env = dict(os.environ, MGPU_BACKEND="gloo", D2D_TRANSPORT="boot", D2D_CHUNKS=chunks, MGPU_SHAPES="small", CUDA_VISIBLE_DEVICES="0")
+    # exchange: auto = pipelined chains (copy-engine pushes) up to 2 ranks per communicator, fused peer stores beyond (the 2 x 4
+    # grid of 8 ranks: both links of a chain are real); "fused" on 4 ranks forces the fused chain onto the 2 x 2 grid
+    env = dict(os.environ, MGPU_BACKEND="gloo", D2D_TRANSPORT="boot", D2D_CHUNKS=chunks, D2D_EXCHANGE=exchange, MGPU_SHAPES="small",
+               CUDA_VISIBLE_DEVICES="0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29540 + world + int(chunks)), os.path.join(ROOT, "tools", "mgpu_check.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+           "--master-port", str(29540 + world + int(chunks) + len(exchange)), os.path.join(ROOT, "tools", "mgpu_check.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "failures 0" in r.stdout
