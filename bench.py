@@ -491,9 +491,11 @@ def main():
             "parity": f"ramp field r2c vs closed form at {n}^3 on {grid[0]}x{grid[1]}: {fwd_err:.2e} (tol {tol:.0e}); "
                       f"round trip {rt_err:.2e}",
             "hbm_floor_ms": (2 * rtot + 10 * ctot) / world / peak / 1e6,
-            "exchange": os.environ.get("D2D_FUSED", "0") == "1" and "fused peer stores" or
-                        (os.environ.get("D2D_P2P", "1") == "0" and "nccl send/recv" or "copy-engine pushes over peer memory, chunk-pipelined")
-                        if world > 1 else None,
+            "exchange": None if world == 1 else (
+                "copy-engine pushes over peer memory, chunk-pipelined with the stages" if any(k.startswith("ce_") for k in prof) and os.environ.get("D2D_PUSH") != "sm"
+                else "exchange kernel (TMA pushes) over peer memory, chunk-pipelined with the stages" if any(k.startswith("ce_") for k in prof)
+                else "fused peer stores of the producer kernels over peer memory" if any(k.startswith("p2p_") and k[4:] in ("x_y", "y_x", "y_z", "z_y") for k in prof)
+                else "NCCL grouped send/recv"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
