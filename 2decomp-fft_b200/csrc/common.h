@@ -115,6 +115,8 @@ struct Ctx {
    size_t work_bytes[kCtxBuffers] = {0, 0, 0, 0};
    void *scratch = nullptr; // global-memory scratch of the two-kernel transforms of very long lines (fft_any.cu)
    size_t scratch_bytes = 0;
+   void *scratch2 = nullptr; // zero-padded lines of the Bluestein transforms (fft_any.cu); their M-point transforms may use `scratch`
+   size_t scratch2_bytes = 0;
    struct P2P *p2p = nullptr; // peer-mapped work buffers + flags (p2p.cpp); null when unused
    // chunk-wise pipelined chains (fft_plan.cpp run_chain_pipe): the exchanges run on their own streams -- one per peer
    // of a communicator for the copy-engine pushes of the peer-memory path, comm_stream for the transports' exchanges

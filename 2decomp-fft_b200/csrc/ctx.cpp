@@ -64,7 +64,7 @@ const void *twiddles_for(int device, int n, int f64, int compact)
    for (int p = 0; p < k->npass; p++) {
       const int R = k->radix[p];
       if (p >= 1) {
-         const int rmax = (compact && R <= 4) ? 1 : R - 1;
+         const int rmax = (compact && (R == 2 || R == 4)) ? 1 : R - 1;
          for (int r = 1; r <= rmax; r++)
             for (long long q = 0; q < ns; q++) {
                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(r * q) / (long double)(ns * R);
@@ -253,6 +253,7 @@ Ctx::~Ctx()
    for (int i = 0; i < kCtxBuffers; i++)
       if (work[i]) cudaFree(work[i]);
    if (scratch) cudaFree(scratch);
+   if (scratch2) cudaFree(scratch2);
    if (stream) cudaStreamDestroy(stream);
 }
 

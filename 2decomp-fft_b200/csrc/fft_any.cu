@@ -13,6 +13,8 @@
 
 namespace d2d {
 
+cudaError_t fft_dispatch(Ctx *ctx, FftArgs &g, int f64, int mode, int kind, int pairvec, bool wide_real); // fft_plan.cpp
+
 namespace {
 struct RootKey {
    int device, n, f64;
@@ -129,11 +131,15 @@ int fft_any_factorize(int n, int *radix, int maxp)
    return np;
 }
 
+void fft_any_release_blue(); // below (Bluestein tables)
 void fft_any_release_all()
 {
-   std::lock_guard<std::mutex> lk(g_root_mutex);
-   for (auto &kv : g_roots) cudaFree(kv.second);
-   g_roots.clear();
+   {
+      std::lock_guard<std::mutex> lk(g_root_mutex);
+      for (auto &kv : g_roots) cudaFree(kv.second);
+      g_roots.clear();
+   }
+   fft_any_release_blue();
 }
 
 // largest transform length the shared-memory kernel takes (one line per block, two buffers + the root table)
@@ -240,11 +246,245 @@ static cudaError_t fft_any_launch_split(Ctx *ctx, const FftArgs &g, int f64, int
    return e;
 }
 
+// ---- Bluestein: lengths with a prime factor beyond the shared-memory kernel --------------------------------------------
+// The reference's generic backend takes ANY length (src/glassman.f90:29-67 falls back to an O(n * factor) loop); here a
+// length that neither fits the shared-memory kernel nor splits into two factors that do becomes a circular convolution of
+// power-of-two length M >= 2n - 1 (chirp-z):  with c[j] = exp(-pi i j^2 / n),
+//    X[k] = c[k] * sum_j (x[j] c[j]) conj(c[k - j])  =  c[k] * IFFT_M( FFT_M(x c, zero-padded) . FFT_M(b) )[k],
+//    b[j] = b[M - j] = conj(c[j]) for j < n, 0 elsewhere.
+// Five launches per chunk of lines through a second scratch array: chirp-in, FFT_M, spectrum product, inverse FFT_M, chirp-out;
+// the M-point transforms run on the compiled power-of-two kernels (or their two-kernel split).  Real transforms use the
+// conversions of the reference's generic backend at the two ends, like the two-kernel split above.
+namespace {
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) blue_in_kernel(const __grid_constant__ FftArgs g, const typename Vec2<T>::type *__restrict__ chirp,
+                                                      typename Vec2<T>::type *__restrict__ scr, int logM, int lines_a, long long l0, long long nl)
+{
+   using T2 = typename Vec2<T>::type;
+   const int n = g.n;
+   const long long total = nl << logM;
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+      const long long l = idx >> logM;
+      const int j = (int)(idx - (l << logM));
+      T2 x = T2{0, 0};
+      if (j < n) {
+         const long long id = l0 + l, b = id / lines_a, a = id - b * lines_a;
+         if constexpr (MODE == MODE_R2C) {
+            x.x = reinterpret_cast<const T *>(g.rptr)[(long long)j * g.rse + a * g.rsa + b * g.rsb];
+         } else if constexpr (MODE == MODE_C2R) { // Hermitian completion (src/fft_generic.f90:320-337)
+            if (2 * j > n) {
+               x = load_piece<T2>(g.in, n - j, a, b);
+               x.y = -x.y;
+            } else {
+               x = load_piece<T2>(g.in, j, a, b);
+               if (j == 0 || 2 * j == n) x.y = 0;
+            }
+         } else {
+            x = load_piece<T2>(g.in, j, a, b);
+         }
+         if (g.backward) x.y = -x.y;
+         if (!g.passthrough) x = cmul(x, chirp[j]);
+      }
+      scr[idx] = x;
+   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) blue_mul_kernel(typename Vec2<T>::type *__restrict__ scr, const typename Vec2<T>::type *__restrict__ bspec, int logM,
+                                                       long long total)
+{
+   const long long mask = (1LL << logM) - 1;
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+      scr[idx] = cmul(scr[idx], bspec[idx & mask]);
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) blue_out_kernel(const __grid_constant__ FftArgs g, const typename Vec2<T>::type *__restrict__ chirp,
+                                                       const typename Vec2<T>::type *__restrict__ scr, int logM, int lines_a, long long l0, long long nl)
+{
+   using T2 = typename Vec2<T>::type;
+   const int n = g.n, nout = (MODE == MODE_R2C) ? n / 2 + 1 : n;
+   const long long total = nl * nout;
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+      const long long l = idx / nout;
+      const int k = (int)(idx - l * nout);
+      const long long id = l0 + l, b = id / lines_a, a = id - b * lines_a;
+      T2 y = scr[(l << logM) + k];
+      if (!g.passthrough) y = cmul(y, chirp[k]);
+      if (g.backward) y.y = -y.y;
+      if constexpr (MODE == MODE_C2R) reinterpret_cast<T *>(g.rptr)[(long long)k * g.rse + a * g.rsa + b * g.rsb] = y.x;
+      else store_piece<T2>(g.out, k, a, b, y);
+   }
+}
+
+struct BlueTab {
+   void *chirp = nullptr, *bspec = nullptr;
+   int logM = 0;
+};
+std::map<RootKey, BlueTab> g_blue;
+
+// chirp c[j] = exp(-pi i j^2 / n) (j^2 reduced mod 2n in integers) and B = FFT_M(b) / M, both in extended precision on the host
+const BlueTab &blue_tables(int device, int n, int f64)
+{
+   std::lock_guard<std::mutex> lk(g_root_mutex);
+   RootKey key{device, n, f64};
+   auto it = g_blue.find(key);
+   if (it != g_blue.end()) return it->second;
+   int logM = 1;
+   while ((1LL << logM) < 2LL * n - 1) logM++;
+   const size_t M = (size_t)1 << logM;
+   const long double pi = 3.14159265358979323846264338327950288L;
+   std::vector<long double> cr(n), ci(n);
+   for (int j = 0; j < n; j++) {
+      const long long r = ((long long)j * j) % (2LL * n);
+      const long double ang = pi * (long double)r / (long double)n;
+      cr[j] = cosl(ang);
+      ci[j] = -sinl(ang);
+   }
+   // b in bit-reversed order, then an in-place radix-2 decimation-in-time transform with a table of M-th roots
+   std::vector<long double> br(M, 0.0L), bi(M, 0.0L), wr(M / 2), wi(M / 2);
+   auto rev = [&](size_t i) { size_t r = 0; for (int t = 0; t < logM; t++) r |= ((i >> t) & 1) << (logM - 1 - t); return r; };
+   for (int j = 0; j < n; j++) {
+      br[rev((size_t)j)] = cr[j]; bi[rev((size_t)j)] = -ci[j];
+      if (j > 0) { br[rev(M - (size_t)j)] = cr[j]; bi[rev(M - (size_t)j)] = -ci[j]; }
+   }
+   for (size_t k = 0; k < M / 2; k++) {
+      const long double ang = -2.0L * pi * (long double)k / (long double)M;
+      wr[k] = cosl(ang); wi[k] = sinl(ang);
+   }
+   for (size_t len = 2; len <= M; len <<= 1) {
+      const size_t half = len / 2, step = M / len;
+      for (size_t i0 = 0; i0 < M; i0 += len)
+         for (size_t k = 0; k < half; k++) {
+            const long double ur = br[i0 + k], ui = bi[i0 + k];
+            const long double xr = br[i0 + k + half], xi = bi[i0 + k + half];
+            const long double tr = xr * wr[k * step] - xi * wi[k * step], ti = xr * wi[k * step] + xi * wr[k * step];
+            br[i0 + k] = ur + tr; bi[i0 + k] = ui + ti;
+            br[i0 + k + half] = ur - tr; bi[i0 + k + half] = ui - ti;
+         }
+   }
+   std::vector<double> hc(2 * (size_t)n), hb(2 * M);
+   for (int j = 0; j < n; j++) { hc[2 * j] = (double)cr[j]; hc[2 * j + 1] = (double)ci[j]; }
+   for (size_t k = 0; k < M; k++) { hb[2 * k] = (double)(br[k] / (long double)M); hb[2 * k + 1] = (double)(bi[k] / (long double)M); }
+   auto upload = [&](const std::vector<double> &h) {
+      void *d = nullptr;
+      const size_t bytes = h.size() / 2 * (f64 ? 16 : 8);
+      D2D_CHECK_CUDA(cudaMalloc(&d, bytes));
+      if (f64) D2D_CHECK_CUDA(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+      else {
+         std::vector<float> hf(h.begin(), h.end());
+         D2D_CHECK_CUDA(cudaMemcpy(d, hf.data(), bytes, cudaMemcpyHostToDevice));
+      }
+      return d;
+   };
+   BlueTab t;
+   t.chirp = upload(hc);
+   t.bspec = upload(hb);
+   t.logM = logM;
+   return g_blue[key] = t;
+}
+
+template <typename T, int MODE>
+cudaError_t blue_run(Ctx *ctx, const FftArgs &g, const BlueTab &t, int lines_a, long long lines, int sms)
+{
+   using T2 = typename Vec2<T>::type;
+   const int f64 = sizeof(T) == 8;
+   const size_t M = (size_t)1 << t.logM;
+   const long long per_chunk = std::max<long long>(1, std::min<long long>(lines, (long long)(ctx->scratch2_bytes / (M * sizeof(T2)))));
+   T2 *scr = reinterpret_cast<T2 *>(ctx->scratch2);
+   const T2 *chirp = reinterpret_cast<const T2 *>(t.chirp), *bspec = reinterpret_cast<const T2 *>(t.bspec);
+   auto grid_for = [&](long long items) { return (unsigned)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)sms * 8)); };
+   for (long long l0 = 0; l0 < lines; l0 += per_chunk) {
+      const long long nl = std::min(per_chunk, lines - l0);
+      const long long total = nl << t.logM;
+      blue_in_kernel<T, MODE><<<grid_for(total), 256, 0, ctx->stream>>>(g, chirp, scr, t.logM, lines_a, l0, nl);
+      if (!g.passthrough) {
+         FftArgs gi{};
+         gi.in.np = gi.out.np = 1;
+         gi.in.e0[0] = gi.out.e0[0] = 0;
+         gi.in.e0[1] = gi.out.e0[1] = (int)M;
+         gi.in.ptr[0] = gi.out.ptr[0] = scr;
+         gi.in.se[0] = gi.out.se[0] = 1;
+         gi.in.sa[0] = gi.out.sa[0] = (long long)M;
+         gi.in.sb[0] = gi.out.sb[0] = 0;
+         gi.na = (int)nl;
+         gi.nb = 1;
+         gi.n = (int)M;
+         gi.sm_limit = g.sm_limit;
+         cudaError_t e = fft_dispatch(ctx, gi, f64, MODE_C2C, KIND_LINE, 0, false);
+         if (e != cudaSuccess) return e;
+         blue_mul_kernel<T><<<grid_for(total), 256, 0, ctx->stream>>>(scr, bspec, t.logM, total);
+         gi.backward = 1;
+         e = fft_dispatch(ctx, gi, f64, MODE_C2C, KIND_LINE, 0, false);
+         if (e != cudaSuccess) return e;
+      }
+      const long long nout = (MODE == MODE_R2C) ? g.n / 2 + 1 : g.n;
+      blue_out_kernel<T, MODE><<<grid_for(nl * nout), 256, 0, ctx->stream>>>(g, chirp, scr, t.logM, lines_a, l0, nl);
+   }
+   return cudaGetLastError();
+}
+
+cudaError_t fft_any_launch_bluestein(Ctx *ctx, const FftArgs &g, int f64, int mode)
+{
+   const int n = g.n;
+   D2D_REQUIRE(n < (1 << 24), "transform length " + std::to_string(n) + " is not supported");
+   const BlueTab &t = blue_tables(ctx->device, n, f64);
+   const size_t M = (size_t)1 << t.logM, ces = f64 ? 16 : 8;
+   const int lines_a = (mode == MODE_C2C) ? g.na : g.na_real; // real transforms: one complex line per real line
+   const long long lines = (long long)lines_a * g.nb;
+   if (lines <= 0) return cudaSuccess;
+   // scratch: whole lines of M points, at most ~1 GiB per chunk of lines (grow-only)
+   const size_t want = std::max<size_t>(M * ces, std::min<size_t>((size_t)lines * M * ces, (size_t)1 << 30));
+   if (want > ctx->scratch2_bytes) {
+      D2D_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->scratch2) D2D_CHECK_CUDA(cudaFree(ctx->scratch2));
+      ctx->scratch2 = nullptr;
+      ctx->scratch2_bytes = 0;
+      D2D_CHECK_CUDA(cudaMalloc(&ctx->scratch2, want));
+      ctx->scratch2_bytes = want;
+   }
+   int sms = 0;
+   D2D_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+   if (mode == MODE_C2C) return f64 ? blue_run<double, MODE_C2C>(ctx, g, t, lines_a, lines, sms) : blue_run<float, MODE_C2C>(ctx, g, t, lines_a, lines, sms);
+   if (mode == MODE_R2C) return f64 ? blue_run<double, MODE_R2C>(ctx, g, t, lines_a, lines, sms) : blue_run<float, MODE_R2C>(ctx, g, t, lines_a, lines, sms);
+   return f64 ? blue_run<double, MODE_C2R>(ctx, g, t, lines_a, lines, sms) : blue_run<float, MODE_C2R>(ctx, g, t, lines_a, lines, sms);
+}
+
+// does n = n1 n2 with both factors within the shared-memory kernel's reach?
+bool any_splits(int n, int lim)
+{
+   for (int d = 2; (long long)d * d <= n; d++)
+      if (n % d == 0 && n / d <= lim) return true; // d <= sqrt(n) <= n / d <= lim
+   return false;
+}
+} // namespace
+
+void fft_any_release_blue()
+{
+   std::lock_guard<std::mutex> lk(g_root_mutex);
+   for (auto &kv : g_blue) {
+      cudaFree(kv.second.chirp);
+      cudaFree(kv.second.bspec);
+   }
+   g_blue.clear();
+}
+
 cudaError_t fft_any_launch(Ctx *ctx, const FftArgs &g, int f64, int mode)
 {
    const int n = g.n;
    D2D_REQUIRE(n >= 1, "transform length must be positive");
-   if (n > fft_any_max_n(f64)) return fft_any_launch_split(ctx, g, f64, mode);
+   // a large prime factor p costs the shared-memory kernel n * p operations per line (its direct p-point DFT); beyond a few
+   // hundred the five sweeps of the chirp-z path are cheaper (D2D_BLUESTEIN_MIN_PRIME moves the threshold, 0 = never)
+   static const int blue_min = getenv("D2D_BLUESTEIN_MIN_PRIME") ? atoi(getenv("D2D_BLUESTEIN_MIN_PRIME")) : 600;
+   if (blue_min > 0 && n > blue_min && !g.passthrough) {
+      int m = n, big = 1;
+      for (int f = 2; (long long)f * f <= m; f++)
+         while (m % f == 0) { big = f; m /= f; }
+      if (m > 1) big = m;
+      if (big > blue_min) return fft_any_launch_bluestein(ctx, g, f64, mode);
+   }
+   if (n > fft_any_max_n(f64)) return any_splits(n, fft_any_max_n(f64)) ? fft_any_launch_split(ctx, g, f64, mode) : fft_any_launch_bluestein(ctx, g, f64, mode);
    FftArgsAny ga{};
    ga.a = g;
    ga.a.tw = roots_for(ctx->device, n, f64);

@@ -19,24 +19,26 @@ using P = Pow2Plan<D2D_N>;
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int pow2_floor(int v) { int p = 1; while (2 * p <= v) p *= 2; return p; } // tile extents stay powers of two for 3 * 2^k / 5 * 2^k lines
 
 // ---- geometry (see DESIGN.md "kernel geometry") ------------------------------------------------
 constexpr int kTargetThreads = 256;
 constexpr int kMaxSmem = 128 * 1024;
 constexpr int kLineBytes = P::N * (int)sizeof(T2);
 // contiguous-line kernel: TX = 1, LY lines per block
-constexpr int LY_LINE = cmax(1, cmin(kTargetThreads / P::T, kMaxSmem / kLineBytes));
+constexpr int LY_LINE = pow2_floor(cmax(1, cmin(kTargetThreads / P::T, kMaxSmem / kLineBytes)));
 // strided-tile kernel: TX adjacent lines so that one row of the tile is 64 B
 constexpr int TX_WANT = 64 / (int)sizeof(T2);
-constexpr int TX_TILE = cmax(1, cmin(TX_WANT, cmin(1024 / P::T, kMaxSmem / kLineBytes)));
-constexpr int LY_TILE = cmax(1, cmin(kTargetThreads / (TX_TILE * P::T), kMaxSmem / (kLineBytes * TX_TILE)));
+constexpr int TX_TILE = pow2_floor(cmax(1, cmin(TX_WANT, cmin(1024 / P::T, kMaxSmem / kLineBytes))));
+constexpr int LY_TILE = pow2_floor(cmax(1, cmin(kTargetThreads / (TX_TILE * P::T), kMaxSmem / (kLineBytes * TX_TILE))));
 // wide tiles (128 B rows) for the stages whose far side is a user array with a huge row pitch
-constexpr int TX_WIDE = cmax(1, cmin(2 * TX_WANT, cmin(1024 / P::T, (200 * 1024) / kLineBytes)));
-constexpr int LY_WIDE = cmax(1, cmin(kTargetThreads / (TX_WIDE * P::T), kMaxSmem / (kLineBytes * TX_WIDE)));
+constexpr int TX_WIDE = pow2_floor(cmax(1, cmin(2 * TX_WANT, cmin(1024 / P::T, (200 * 1024) / kLineBytes))));
+constexpr int LY_WIDE = pow2_floor(cmax(1, cmin(kTargetThreads / (TX_WIDE * P::T), kMaxSmem / (kLineBytes * TX_WIDE))));
 constexpr int PADK = P::R0; // one padding element per first-pass butterfly (bank-conflict model: tools/smem_conflicts.py)
 
 // resident blocks per SM the v1 kernels are compiled for; 32-element plans need the whole register file of one block
-constexpr int minb_for(int threads) { return P::E >= 32 ? (D2D_F64 ? 1 : 2) : cmax(1, (D2D_F64 ? 512 : 768) / threads); }
+// (20 / 24 fp64 elements per thread -- the 5 * 2^k / 3 * 2^k plans -- spill at the 128 registers of two 256-thread blocks)
+constexpr int minb_for(int threads) { return P::E >= 32 ? (D2D_F64 ? 1 : 2) : (P::E >= 20 && D2D_F64) ? 1 : cmax(1, (D2D_F64 ? 512 : 768) / threads); }
 
 template <int TX, int LY, int MODE, bool PAIRVEC, bool LM = false> struct Inst {
    using G = KernelGeom<real_t, P, TX, LY, PADK, LM>;

@@ -242,7 +242,12 @@ template <typename T> struct Bfly<T, 32> {
    static constexpr int out_idx(int r) { return (r & 1) * 16 + Bfly<T, 16>::out_idx(r >> 1); }
 };
 
-// ---- radix plans for power-of-two n: E elements per thread, T = n/E threads per line ------------
+} // namespace d2d
+#include "fft_bfly_mixed.cuh" // radices 3, 5, 6, 10, 12, 20, 24
+namespace d2d {
+
+// ---- radix plans: E elements per thread, T = n/E threads per line; every radix divides E --------
+// (the name dates from the time when only powers of two had compiled kernels)
 template <int N> struct Pow2Plan;
 #define D2D_PLAN(N_, E_, A, B, C, D)                                                                                   \
    template <> struct Pow2Plan<N_> {                                                                                   \
@@ -275,6 +280,27 @@ D2D_PLAN(2048, 16, 16, 16, 8, 1)
 D2D_PLAN(4096, 16, 16, 16, 16, 1)
 D2D_PLAN(8192, 16, 16, 16, 16, 2)
 D2D_PLAN(16384, 16, 16, 16, 16, 4)
+// 3 * 2^k: 24 elements per thread (12 below 96), first pass radix 24 = 3 x 8, then radix 8 / 4 passes (radix-4 passes keep
+// one twiddle per butterfly in the TMA kernels: the kernels are bound by the shared-memory pipe, not by the FP64 pipe)
+D2D_PLAN(6, 6, 6, 1, 1, 1)
+D2D_PLAN(12, 12, 12, 1, 1, 1)
+D2D_PLAN(24, 24, 24, 1, 1, 1)
+D2D_PLAN(48, 12, 12, 4, 1, 1)
+D2D_PLAN(96, 24, 24, 4, 1, 1)
+D2D_PLAN(192, 24, 24, 8, 1, 1)
+D2D_PLAN(384, 24, 24, 4, 4, 1)
+D2D_PLAN(768, 24, 24, 8, 4, 1)
+D2D_PLAN(1536, 24, 24, 8, 8, 1)
+D2D_PLAN(3072, 24, 24, 8, 4, 4)
+// 5 * 2^k: 20 elements per thread (radices 20 = 5 x 4, 4, 2)
+D2D_PLAN(10, 10, 10, 1, 1, 1)
+D2D_PLAN(20, 20, 20, 1, 1, 1)
+D2D_PLAN(40, 20, 20, 2, 1, 1)
+D2D_PLAN(80, 20, 20, 4, 1, 1)
+D2D_PLAN(160, 20, 20, 4, 2, 1)
+D2D_PLAN(320, 20, 20, 4, 4, 1)
+D2D_PLAN(640, 20, 20, 4, 4, 2)
+D2D_PLAN(1280, 20, 20, 4, 4, 4)
 #undef D2D_PLAN
 // (A one-exchange fp32 plan 2048 = 64 . 32 with 64 elements per thread was measured at 2048^3 fp32 on one B200: 109.8 ms
 // per pair against 109.0 ms with 16 . 16 . 8 -- three variants spill -- so single precision keeps the plans above.)
@@ -289,7 +315,7 @@ template <class P> struct PlanInfo {
 };
 
 // shared-memory index of line position p: one padding element every PADK elements
-template <int PADK> __device__ __forceinline__ constexpr int padix(int p) { return PADK > 0 ? p + p / (PADK > 0 ? PADK : 1) : p; }
+template <int PADK> D2D_HD constexpr int padix(int p) { return PADK > 0 ? p + p / (PADK > 0 ? PADK : 1) : p; }
 
 template <typename T2> __device__ __forceinline__ T2 ldg_nc(const T2 *p);
 template <> __device__ __forceinline__ double2 ldg_nc<double2>(const double2 *p) { return __ldg(p); }
@@ -326,7 +352,7 @@ template <typename T, class P, int PASS, int SP, int PADK, bool TWS> struct Pass
    static constexpr int E = P::E, TPL = P::T, N = P::N;
    static constexpr int R = PI::radix(PASS), NS = PI::ns(PASS), NB = E / R; // NB butterflies per thread
 
-   static __device__ __forceinline__ void twiddle(T2 *v, int j, const T2 *__restrict__ tw)
+   static D2D_HD void twiddle(T2 *v, int j, const T2 *__restrict__ tw)
    {
       if (PASS == 0) return;
 #pragma unroll
@@ -341,11 +367,11 @@ template <typename T, class P, int PASS, int SP, int PADK, bool TWS> struct Pass
          }
       }
    }
-   static __device__ __forceinline__ void butterflies(T2 *v)
+   static D2D_HD void butterflies(T2 *v)
    {
       run_b<0>(v);
    }
-   template <int U> static __device__ __forceinline__ void run_b(T2 *v)
+   template <int U> static D2D_HD void run_b(T2 *v)
    {
       if constexpr (U < NB) {
          Bfly<T, R>::template run<U, NB>(v);
@@ -353,7 +379,7 @@ template <typename T, class P, int PASS, int SP, int PADK, bool TWS> struct Pass
       }
    }
    // scatter the outputs to shared memory at their Stockham positions
-   static __device__ __forceinline__ void scatter(const T2 *v, int j, T2 *lsm)
+   static D2D_HD void scatter(const T2 *v, int j, T2 *lsm)
    {
 #pragma unroll
       for (int u = 0; u < NB; u++) {
@@ -364,7 +390,7 @@ template <typename T, class P, int PASS, int SP, int PADK, bool TWS> struct Pass
       }
    }
    // last pass: put output slot s = u + r*NB into w[s] (compile-time permutation)
-   static __device__ __forceinline__ void unpermute(const T2 *v, T2 *w)
+   static D2D_HD void unpermute(const T2 *v, T2 *w)
    {
 #pragma unroll
       for (int u = 0; u < NB; u++)

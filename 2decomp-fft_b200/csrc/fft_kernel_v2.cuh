@@ -77,7 +77,7 @@ struct FftArgs2 {
 // ---- twiddle layout with compact radix-2/4 tables ---------------------------------------------------
 template <class P> struct PlanInfo2 {
    using PI = PlanInfo<P>;
-   static constexpr bool compact(int p) { return p >= 1 && PI::radix(p) <= 4; }
+   static constexpr bool compact(int p) { return p >= 1 && (PI::radix(p) == 2 || PI::radix(p) == 4); }
    static constexpr int entries(int p) { return p < 1 ? 0 : (compact(p) ? PI::ns(p) : (PI::radix(p) - 1) * PI::ns(p)); }
    static constexpr int tw_off(int p) { return p <= 1 ? 0 : tw_off(p - 1) + entries(p - 1); }
    static constexpr int tw_total = tw_off(PI::npass);

@@ -44,6 +44,26 @@ struct Plan {
 
 static const int *pencil_size(const Decomp &d, int p) { return p == 0 ? d.xsz : p == 1 ? d.ysz : d.zsz; }
 
+// Picks the kernel of one batched 1-D transform described by g (maps, batch extents, n, flags) and launches it on the
+// context's stream: a compiled plan (TMA-staged when the alignment rules hold, cp.async otherwise) or the any-length kernel.
+// Also the inner transform of the Bluestein path (fft_any.cu).
+cudaError_t fft_dispatch(Ctx *ctx, FftArgs &g, int f64, int mode, int kind, int pairvec, bool wide_real)
+{
+   const int n = g.n;
+   const FftKernelInfo *k = nullptr;
+   if (wide_real) k = fft_find(n, f64, KIND_TILE_WIDE, mode, pairvec);
+   // inputs that are contiguous along the transform axis land through the line-major kernels
+   const bool line_like = kind == KIND_TILE && ((mode == MODE_C2C && g.in.se[0] == 1) || (mode == MODE_R2C && g.rse == 1));
+   if (!k && line_like) k = fft_find(n, f64, kind, mode, pairvec, 1);
+   if (!k) k = fft_find(n, f64, kind, mode, pairvec);
+   if (k) g.tw = twiddles_for(ctx->device, n, f64);
+   cudaError_t e = cudaSuccess;
+   if (!k) e = fft_any_launch(ctx, g, f64, mode); // no compiled plan for this length: mixed-radix shared-memory kernel
+   else if (!fft_v2_try_launch(ctx, g, f64, mode, &e)) e = k->launch(g, ctx->stream);
+   if (e == cudaSuccess) ctx->launches++;
+   return e;
+}
+
 // One batched 1-D stage along `pencil` of the complex-side decomp dc (real side: dr, R2C/C2R only).
 // This is c2c_1m_{x,y,z} / r2c_1m_{x,z} / c2r_1m_{x,z} (src/fft_cufft.f90:489-671) fused with the
 // neighbouring mem_split_* / mem_merge_* through the maps.  `chain`: the stage is part of a 3-D
@@ -118,24 +138,14 @@ static void run_stage(Ctx *ctx, int f64, int mode, int pencil, const Decomp &dc,
    }
    g.n = n;
    if (lines == 0) return;
-   const FftKernelInfo *k = nullptr;
    static const bool wide = getenv("D2D_WIDE_REAL_TILES") && atoi(getenv("D2D_WIDE_REAL_TILES")) != 0;
-   if (wide && chain && mode != MODE_C2C && pencil == 2 && pairvec) k = fft_find(n, f64, KIND_TILE_WIDE, mode, pairvec);
-   // inputs that are contiguous along the transform axis land through the line-major kernels
-   const bool line_like = kind == KIND_TILE && ((mode == MODE_C2C && in.se[0] == 1) || (mode == MODE_R2C && g.rse == 1));
-   if (!k && line_like) k = fft_find(n, f64, kind, mode, pairvec, 1);
-   if (!k) k = fft_find(n, f64, kind, mode, pairvec);
-   if (k) g.tw = twiddles_for(ctx->device, n, f64);
    static const char *axes = "xyz";
    char label[32];
    snprintf(label, sizeof(label), "fft_%s_%c%s", mode == MODE_C2C ? "c2c" : mode == MODE_R2C ? "r2c" : "c2r", axes[pencil],
             (mode == MODE_C2C && chain) ? (backward ? "_bwd" : "_fwd") : "");
    ProfScope ps(ctx, label, bytes);
-   cudaError_t e = cudaSuccess;
-   if (!k) e = fft_any_launch(ctx, g, f64, mode); // not a compiled power of two: mixed-radix shared-memory kernel
-   else if (!fft_v2_try_launch(ctx, g, f64, mode, &e)) e = k->launch(g, ctx->stream);
+   const cudaError_t e = fft_dispatch(ctx, g, f64, mode, kind, pairvec, wide && chain && mode != MODE_C2C && pencil == 2 && pairvec);
    if (e != cudaSuccess) throw Error(1000 + (int)e, std::string("FFT kernel launch failed: ") + cudaGetErrorString(e));
-   ctx->launches++;
 }
 
 struct StageDef {

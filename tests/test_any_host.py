@@ -22,3 +22,19 @@ def test_any_length_pass_arithmetic_on_host(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
     last = r.stdout.strip().splitlines()[-1]
     assert last.startswith("worst fp64"), last
+
+
+def test_compiled_plans_pass_arithmetic_on_host(tmp_path):
+    """Every compiled radix plan (powers of two, 3 * 2^k, 5 * 2^k): the PassOp / Bfly code of csrc/fft_kernel.cuh that the
+    kernels run, with the threads of a line emulated one after the other, against a long-double DFT
+    (tools/micro/test_plans_host.cu)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "test_plans_host"
+    src = os.path.join(ROOT, "tools", "micro", "test_plans_host.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-diag-suppress", "128,177", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-o", str(exe), src], check=True, capture_output=True, timeout=900)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.strip().splitlines()[-1].startswith("worst fp64")
