@@ -72,16 +72,17 @@ const void *roots_for(int device, int n, int f64)
    return dptr;
 }
 
-template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, size_t smem, cudaStream_t st)
+template <typename T, int MODE, bool BIG> cudaError_t launch_any_build(const FftArgsAny &ga, size_t smem, cudaStream_t st)
 {
-   auto kern = fft_any_kernel<T, MODE>;
+   auto kern = fft_any_kernel<T, MODE, BIG>;
+   constexpr int threads = BIG ? kAnyThreadsBig : kAnyThreads;
    // per-device caches (function attributes belong to a device)
    static bool smem_set_of[kMaxDevices] = {false};
    static int sms_of[kMaxDevices] = {0};
    int dev = 0;
    if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-   if (smem + 4096 > 48 * 1024 && !smem_set_of[dev]) { // the kernel also has ~2 KB of static shared memory (line tables)
+   if (smem + 4096 > 48 * 1024 && !smem_set_of[dev]) { // the kernel also has ~3 KB of static shared memory (line tables)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemMax);
       if (e != cudaSuccess) return e;
       smem_set_of[dev] = true;
@@ -92,7 +93,7 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
       if (e != cudaSuccess) return e;
    }
    int per_sm = 0;
-   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAnyThreads, smem);
+   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
    if (e != cudaSuccess) return e;
    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
    const long long total = (long long)ga.a.na * ga.a.nb;
@@ -100,34 +101,34 @@ template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, siz
    if (groups <= 0) return cudaSuccess;
    const long long resident = (long long)sms * per_sm;
    const unsigned blocks = (unsigned)(groups < resident ? groups : resident);
-   kern<<<blocks, kAnyThreads, smem, st>>>(ga);
+   kern<<<blocks, threads, smem, st>>>(ga);
    return cudaGetLastError();
+}
+template <typename T, int MODE> cudaError_t launch_any(const FftArgsAny &ga, size_t smem, cudaStream_t st)
+{
+   return ga.big ? launch_any_build<T, MODE, true>(ga, smem, st) : launch_any_build<T, MODE, false>(ga, smem, st);
 }
 } // namespace
 
-// factors of n in pass order: primes above kAnyMaxFixedOdd first (the first of them needs no twiddles), then 16s and the
-// remaining power of two, then 9s, 3s, 5s, 7s, 11s, 13s
-int fft_any_factorize(int n, int *radix, int maxp)
+// radices of n in pass order (fft_any.cuh any_factorize) and the build of the kernel that runs them: the big build (radices
+// up to 31, 128 threads) when it needs fewer passes or turns a run-time radix (a prime in 17..31) into a register one.
+// D2D_ANY_BIG: 0 never, 1 as described (default), 2 whenever a radix above 16 helps or not
+int fft_any_factorize(int n, int *radix, int maxp, int *big)
 {
-   int np = 0;
-   auto push = [&](int r) {
-      if (np < maxp) radix[np] = r;
-      np++;
-   };
-   int small = 1; // product of the factors with register butterflies
-   int m = n;
-   for (int f = 2; f <= kAnyMaxFixedOdd; f++)
-      while (m % f == 0) { m /= f; small *= f; }
-   for (int f = kAnyMaxFixedOdd + 2; (long long)f * f <= m; f += 2)
-      while (m % f == 0) { push(f); m /= f; }
-   if (m > 1) push(m);
-   while (small % 16 == 0) { push(16); small /= 16; }
-   if (small % 8 == 0) { push(8); small /= 8; }
-   if (small % 4 == 0) { push(4); small /= 4; }
-   if (small % 2 == 0) { push(2); small /= 2; }
-   while (small % 9 == 0) { push(9); small /= 9; }
-   for (int f = 3; f <= kAnyMaxFixedOdd; f += 2)
-      while (small % f == 0) { push(f); small /= f; }
+   static const int mode = getenv("D2D_ANY_BIG") ? atoi(getenv("D2D_ANY_BIG")) : 1;
+   int rs[kMaxAnyPass], rb[kMaxAnyPass];
+   bool nb = false;
+   const int ns = any_factorize(n, rs, kMaxAnyPass, false, nullptr);
+   const int nbg = any_factorize(n, rb, kMaxAnyPass, true, &nb);
+   bool use_big = false;
+   if (mode >= 1 && nb && nbg <= kMaxAnyPass) {
+      bool runtime_small = false; // a prime in 17..31 that the small build would run from shared memory
+      for (int i = 0; i < ns && i < kMaxAnyPass; i++) runtime_small = runtime_small || (rs[i] > kAnyMaxFixedSmall && rs[i] <= kAnyMaxFixed);
+      use_big = mode >= 2 || nbg < ns || runtime_small;
+   }
+   const int np = use_big ? nbg : ns;
+   for (int i = 0; i < np && i < maxp; i++) radix[i] = use_big ? rb[i] : rs[i];
+   if (big) *big = use_big ? 1 : 0;
    return np;
 }
 
@@ -151,8 +152,9 @@ static size_t configure_any(FftArgsAny &ga, int f64, int mode, bool split_step)
    const FftArgs &g = ga.a;
    const int n = g.n;
    const size_t ces = f64 ? 16 : 8;
-   ga.npass = fft_any_factorize(n, ga.radix, kMaxAnyPass);
+   ga.npass = fft_any_factorize(n, ga.radix, kMaxAnyPass, &ga.big);
    D2D_REQUIRE(ga.npass <= kMaxAnyPass, "too many factors");
+   const int max_lines = ga.big ? kAnyThreadsBig : kAnyThreads; // at most one line per thread
    ga.pitch = n | 1;
    if (!split_step) { // which axis is unit-stride on each side
       if (mode == MODE_R2C) ga.in_fast_a = (g.rsa == 1 && g.rse != 1);
@@ -167,7 +169,7 @@ static size_t configure_any(FftArgsAny &ga, int f64, int mode, bool split_step)
    static const int row_bytes = getenv("D2D_ANY_ROW_BYTES") ? atoi(getenv("D2D_ANY_ROW_BYTES")) : 128; // experiments: 64 halves the tile
    const int want_rows_log2 = pow2_ceil((long long)(std::max(16, row_bytes) / (int)ces));
    int ll = std::max(want_rows_log2, pow2_ceil((2048 + n - 1) / n));
-   ll = std::min(ll, pow2_ceil(kAnyMaxLines));
+   ll = std::min(ll, pow2_ceil(max_lines));
    ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
    while (ll > 0 && smem_of(1 << ll) > kAnySmemBudget) ll--;
    // two blocks per SM (one loads / stores while the other computes) are worth more than 128-byte rows: 510^3 pair 14.4 ->

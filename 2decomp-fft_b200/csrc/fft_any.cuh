@@ -7,14 +7,21 @@
 // src/fft_cufft.f90:489-671 (CPU twin: src/fft_generic.f90:112-384 over src/glassman.f90) fused with
 // mem_split_* / mem_merge_* of src/transpose_*.f90 through the piece maps.
 //
-// Algorithm: mixed-radix Stockham autosort between two shared-memory buffers, one pass per factor of n.
-//   * factors 16, 8, 4, 2: the register butterflies of the power-of-two kernels;
-//   * odd factors 3..13: register DFT using the conjugate symmetry of the coefficients (inputs r and R-r are
+// Algorithm: mixed-radix Stockham autosort between two shared-memory buffers, one pass per RADIX, where the factors of n
+// are fused into as few register-resident radices as possible (any_factorize below): every pass is a round trip through
+// shared memory, which is what bounds this kernel.
+//   * radices 16, 8, 4, 2 and 6, 10, 12, 15, 20, 24, 30: the register butterflies of the compiled kernels
+//     (fft_kernel.cuh, fft_bfly_mixed.cuh), e.g. 510 = 17 . 30 is two passes, 1000 = 25 . 20 . 2 three;
+//   * odd radices 3..31: register DFT using the conjugate symmetry of the coefficients (inputs r and R-r are
 //     combined first, outputs k and R-k come out of the same two real-weighted sums: half the multiplies);
 //   * any larger prime R: direct R-point DFT from shared memory with the same pairing, one pair of outputs
-//     (k, R-k) per work item -- O(n * sum of factors) work like the reference's Glassman routine, which
-//     is what keeps e.g. n = 17 * 2^k usable.  These passes run FIRST (no twiddles when nothing precedes them);
-//     a second large prime gets its twiddles applied in a separate in-place sweep.
+//     (k, R-k) per work item -- O(n * sum of factors) work like the reference's Glassman routine.  These passes run
+//     FIRST (no twiddles when nothing precedes them); a second large prime gets its twiddles applied in a separate
+//     in-place sweep.  (Lengths whose largest prime factor exceeds a few hundred take the chirp-z path of fft_any.cu.)
+//   * odd radices run before even ones: the scatter of a first pass with an even radix R lands R elements apart (bank
+//     conflicts of degree gcd(R, 8)), an odd one is conflict-free and leaves an odd sub-transform length for the rest.
+// Two builds of the kernel: radices <= 16 in 256 threads and 128 registers; radices up to 31 ("big") in 128 threads and
+// 255 registers -- two resident blocks per SM either way (one loads / stores while the other computes).
 // All twiddles and DFT coefficients are n-th roots of unity, so ONE table W[k] = exp(-2 pi i k / n)
 // (computed in extended precision on the host) staged in shared memory serves every pass.
 // A block owns 2^lines_log2 adjacent lines; lanes run along whichever axis is unit-stride in global memory
@@ -30,14 +37,114 @@
 namespace d2d {
 
 constexpr int kMaxAnyPass = 32;
-constexpr int kAnyThreads = 256;
-constexpr int kAnyMaxLines = 256;    // lines per block (power of two; 256 = one thread per line)
-constexpr int kAnyMaxFixedOdd = 13;  // largest odd radix with a register butterfly
+constexpr int kAnyThreads = 256;     // "small" build; the "big" build runs kAnyThreadsBig
+constexpr int kAnyThreadsBig = 128;
+constexpr int kAnyMaxLines = 256;    // lines per block (power of two, at most one thread per line)
+constexpr int kAnyMaxFixedSmall = 16; // largest register radix of the small build
+constexpr int kAnyMaxFixed = 31;      // ... of the big build
+
+// radices with a register butterfly: X(R) for every R of the small build / the additional ones of the big build
+#define D2D_ANY_RADICES_SMALL(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(15) X(16)
+#define D2D_ANY_RADICES_BIG(X) X(17) X(19) X(20) X(23) X(24) X(25) X(27) X(29) X(30) X(31)
+
+inline bool any_radix_is_fixed(int R, bool big)
+{
+#define D2D_X(r) if (R == r) return true;
+   D2D_ANY_RADICES_SMALL(D2D_X)
+   if (big) { D2D_ANY_RADICES_BIG(D2D_X) }
+#undef D2D_X
+   return false;
+}
+
+// Pass radices of an n-point transform, in pass order.  Primes above the largest register radix first (run-time radix; the
+// first of them needs no twiddles), then the odd register radices in decreasing order, then the even ones in decreasing
+// order.  The factors 2, 3, 5 are fused into the radices 2 3 4 5 6 8 9 10 12 15 16 (and 20 24 25 27 30, big build) by an
+// exhaustive search for the fewest passes; among those the plan with the largest odd radix, then the largest smallest
+// radix (balanced passes) wins.  Returns the number of passes (radix[] holds at most maxp of them); *needs_big: a radix
+// above kAnyMaxFixedSmall occurs.
+struct AnyFuse {
+   int best[kMaxAnyPass], nbest = 0, cur[kMaxAnyPass];
+   long long best_cost = -1;
+   bool big = false;
+   void search(int c2, int c3, int c5, int depth, int last)
+   {
+      if (c2 == 0 && c3 == 0 && c5 == 0) {
+         int odd = 0, mn = 1 << 30;
+         for (int i = 0; i < depth; i++) {
+            if (cur[i] % 2 && cur[i] > odd) odd = cur[i];
+            if (cur[i] < mn) mn = cur[i];
+         }
+         const long long cost = (long long)depth * 10000 - odd * 100 - (depth ? mn : 0);
+         if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            nbest = depth;
+            for (int i = 0; i < depth; i++) best[i] = cur[i];
+         }
+         return;
+      }
+      if (depth >= kMaxAnyPass || (best_cost >= 0 && (long long)(depth + 1) * 10000 - 3100 > best_cost)) return;
+      static const int cand[16][4] = {{30, 1, 1, 1}, {27, 0, 3, 0}, {25, 0, 0, 2}, {24, 3, 1, 0}, {20, 2, 0, 1}, {16, 4, 0, 0}, {15, 0, 1, 1}, {12, 2, 1, 0},
+                                      {10, 1, 0, 1}, {9, 0, 2, 0},  {8, 3, 0, 0},  {6, 1, 1, 0},  {5, 0, 0, 1},  {4, 2, 0, 0},  {3, 0, 1, 0},  {2, 1, 0, 0}};
+      for (int i = 0; i < 16; i++) {
+         const int r = cand[i][0];
+         if (r > last || (!big && r > kAnyMaxFixedSmall)) continue; // non-increasing radices: every multiset once
+         if (cand[i][1] > c2 || cand[i][2] > c3 || cand[i][3] > c5) continue;
+         cur[depth] = r;
+         search(c2 - cand[i][1], c3 - cand[i][2], c5 - cand[i][3], depth + 1, r);
+      }
+   }
+};
+
+inline int any_factorize(int n, int *radix, int maxp, bool allow_big, bool *needs_big)
+{
+   int np = 0;
+   auto push = [&](int r) {
+      if (np < maxp) radix[np] = r;
+      np++;
+   };
+   int m = n, c2 = 0, c3 = 0, c5 = 0;
+   while (m % 2 == 0) { m /= 2; c2++; }
+   while (m % 3 == 0) { m /= 3; c3++; }
+   while (m % 5 == 0) { m /= 5; c5++; }
+   int fixed[64], nfixed = 0; // register radices, sorted below
+   const int top = allow_big ? kAnyMaxFixed : 13;
+   for (int f = 7; (long long)f * f <= m; f += 2)
+      while (m % f == 0) {
+         if (f <= top) fixed[nfixed++] = f;
+         else push(f);
+         m /= f;
+      }
+   if (m > 1) {
+      if (m <= top) fixed[nfixed++] = m;
+      else push(m);
+   }
+   AnyFuse fz;
+   fz.big = allow_big;
+   fz.search(c2, c3, c5, 0, 1 << 30);
+   for (int i = 0; i < fz.nbest && nfixed < 64; i++) fixed[nfixed++] = fz.best[i];
+   // odd radices first, each group in decreasing order
+   for (int i = 1; i < nfixed; i++)
+      for (int j = i; j > 0; j--) {
+         const int a = fixed[j], b = fixed[j - 1];
+         const bool before = (a % 2 != b % 2) ? (a % 2 == 1) : (a > b);
+         if (!before) break;
+         fixed[j] = b;
+         fixed[j - 1] = a;
+      }
+   for (int i = 0; i < nfixed; i++) push(fixed[i]);
+   if (needs_big) {
+      *needs_big = false;
+      for (int i = 0; i < np && i < maxp; i++)
+         if (radix[i] > kAnyMaxFixedSmall && radix[i] <= kAnyMaxFixed) *needs_big = true;
+   }
+   return np;
+}
 
 struct FftArgsAny {
    FftArgs a;                 // a.tw = W[k] = exp(-2 pi i k / n), k in [0, n)
    int npass;
    int radix[kMaxAnyPass];
+   int big;                   // 1: the build with radices up to 31 in 128 threads runs it
    int lines_log2;            // complex lines per block = 1 << lines_log2
    int pitch;                 // shared-memory pitch of a line, in complex elements (odd)
    int in_fast_a, out_fast_a; // 1: adjacent lines (axis a) are contiguous in global memory on that side
@@ -87,7 +194,7 @@ template <typename T, int R> D2D_HD void any_bfly_fixed(const typename Vec2<T>::
 #pragma unroll
       for (int r = 1; r < R; r++) x[r] = cmul(src[jj + r * M], W[qs * r]);
    }
-   if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
+   if constexpr (R == 2 || R == 4 || R == 8 || R == 16 || R == 6 || R == 10 || R == 12 || R == 15 || R == 20 || R == 24 || R == 30) {
       Bfly<T, R>::template run<0, 1>(x);
 #pragma unroll
       for (int k = 0; k < R; k++) dst[base + k * Ns] = x[Bfly<T, R>::out_idx(k)];
@@ -97,7 +204,7 @@ template <typename T, int R> D2D_HD void any_bfly_fixed(const typename Vec2<T>::
       static_assert(R % 2 == 1, "odd radix expected");
       constexpr int H = (R - 1) / 2;
       T wc[H + 1], ws[H + 1]; // c_m, s_m for m = 0..H (c_{R-m} = c_m, s_{R-m} = -s_m)
-      wc[0] = (T)1; // m = r k mod R is 0 only for composite R (9)
+      wc[0] = (T)1; // m = r k mod R is 0 only for composite R (9, 25, 27)
       ws[0] = (T)0;
 #pragma unroll
       for (int m = 1; m <= H; m++) {
@@ -173,8 +280,12 @@ __device__ __forceinline__ void any_pass_fixed(const typename Vec2<T>::type *src
    for (int jj = pt; jj < M; jj += TL) any_bfly_fixed<T, R>(src, dst, W, n, Ns, rNs, jj);
 }
 
-template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) fft_any_kernel(const __grid_constant__ FftArgsAny ga)
+template <typename T, int MODE, bool BIG>
+__global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any_kernel(const __grid_constant__ FftArgsAny ga)
 {
+   constexpr int kThreads = BIG ? kAnyThreadsBig : kAnyThreads;
+   constexpr int kLogThreads = BIG ? 7 : 8;
+   static_assert(kThreads == (1 << kLogThreads), "thread indexing assumes a power of two");
    using T2 = typename Vec2<T>::type;
    const FftArgs &g = ga.a;
    const int n = g.n, LL = ga.lines_log2, L = 1 << LL, pitch = ga.pitch;
@@ -187,14 +298,13 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
    __shared__ int line_sub[kAnyMaxLines];                     // split steps: the sub-index of the virtual batch index
    const int split = (MODE == MODE_C2C && ga.split > 1) ? ga.split : 1;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   constexpr int NW = kAnyThreads / 32;
+   constexpr int NW = kThreads / 32;
    // pass identity: TL threads per line
-   const int TL = kAnyThreads >> LL;
-   const int pl = tid >> (8 - LL), pt = tid & (TL - 1); // kAnyThreads == 256
-   static_assert(kAnyThreads == 256, "thread indexing assumes 256 threads");
+   const int TL = kThreads >> LL;
+   const int pl = tid >> (kLogThreads - LL), pt = tid & (TL - 1);
    {
       const T2 *__restrict__ wg = reinterpret_cast<const T2 *>(g.tw);
-      for (int i = tid; i < n; i += kAnyThreads) W[i] = ldg_nc(wg + i);
+      for (int i = tid; i < n; i += kThreads) W[i] = ldg_nc(wg + i);
    }
    const long long total = (long long)g.na * g.nb; // complex lines (pairs of real lines for r2c / c2r)
    const long long ngroups = (total + L - 1) >> LL;
@@ -224,7 +334,7 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
       auto for_each = [&](int len, bool fast_a, auto &&fn) {
          if (fast_a) {
             const int items = len << LL;
-            for (int i = tid; i < items; i += kAnyThreads) fn(i & (L - 1), i >> LL);
+            for (int i = tid; i < items; i += kThreads) fn(i & (L - 1), i >> LL);
          } else {
             for (int l = warp; l < L; l += NW)
                for (int e = lane; e < len; e += 32) fn(l, e);
@@ -296,18 +406,23 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
          for (int p = 0; p < ga.npass; p++) {
             const int R = ga.radix[p];
             const float rNs = 1.0f / (float)Ns;
+            bool done = true;
             switch (R) {
-            case 2: any_pass_fixed<T, 2>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 3: any_pass_fixed<T, 3>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 4: any_pass_fixed<T, 4>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 5: any_pass_fixed<T, 5>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 7: any_pass_fixed<T, 7>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 8: any_pass_fixed<T, 8>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 9: any_pass_fixed<T, 9>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 11: any_pass_fixed<T, 11>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 13: any_pass_fixed<T, 13>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            case 16: any_pass_fixed<T, 16>(src, dst, W, n, Ns, rNs, pt, TL); break;
-            default: {
+#define D2D_X(r) case r: any_pass_fixed<T, r>(src, dst, W, n, Ns, rNs, pt, TL); break;
+               D2D_ANY_RADICES_SMALL(D2D_X)
+            default: done = false;
+            }
+            if constexpr (BIG) {
+               if (!done) {
+                  done = true;
+                  switch (R) {
+                     D2D_ANY_RADICES_BIG(D2D_X)
+                  default: done = false;
+                  }
+               }
+            }
+#undef D2D_X
+            if (!done) {
                const int M = n / R, H = (R - 1) / 2;
                if (Ns > 1) { // twiddles in place: src[jj + r M] *= W[q r s]
                   const int s = n / (Ns * R);
@@ -324,7 +439,6 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kAnyThreads) f
                   const int kp = any_div(i, M, rM), jj = i - kp * M;
                   any_pair_runtime<T>(src, dst, W, n, R, Ns, rNs, jj, kp);
                }
-            }
             }
             __syncthreads();
             T2 *t = src; src = dst; dst = t;

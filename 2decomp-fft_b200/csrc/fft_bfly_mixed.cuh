@@ -1,4 +1,4 @@
-// fft_bfly_mixed.cuh -- register butterflies for the radices 3, 5 and their products with powers of two (6, 10, 12, 20, 24).
+// fft_bfly_mixed.cuh -- register butterflies for the radices 3, 5 and their products (6, 10, 12, 15, 20, 24, 30).
 //
 // Included by fft_kernel.cuh right after the power-of-two butterflies.  With them the compiled, register-resident
 // kernels (fft_kernel.cuh cp.async kernels, fft_kernel_v2.cuh TMA kernels) also cover the lengths 3 * 2^k and 5 * 2^k
@@ -127,5 +127,7 @@ template <typename T> struct Bfly<T, 12> : BflyCT<T, 3, 4> {};
 template <typename T> struct Bfly<T, 24> : BflyCT<T, 3, 8> {};
 template <typename T> struct Bfly<T, 10> : BflyCT<T, 5, 2> {};
 template <typename T> struct Bfly<T, 20> : BflyCT<T, 5, 4> {};
+template <typename T> struct Bfly<T, 15> : BflyCT<T, 3, 5> {};  // any-length kernel only (fft_any.cuh)
+template <typename T> struct Bfly<T, 30> : BflyCT<T, 2, 15> {}; // any-length kernel only
 
 } // namespace d2d

@@ -8,35 +8,18 @@
 
 #include "../../2decomp-fft_b200/csrc/fft_any.cuh"
 
-namespace d2d {
-// the factorisation of fft_any.cu, restated so that this file builds alone
-static int factorize(int n, int *radix, int maxp)
-{
-   int np = 0;
-   auto push = [&](int r) { if (np < maxp) radix[np] = r; np++; };
-   int small = 1, m = n;
-   for (int f = 2; f <= kAnyMaxFixedOdd; f++)
-      while (m % f == 0) { m /= f; small *= f; }
-   for (int f = kAnyMaxFixedOdd + 2; (long long)f * f <= m; f += 2)
-      while (m % f == 0) { push(f); m /= f; }
-   if (m > 1) push(m);
-   while (small % 16 == 0) { push(16); small /= 16; }
-   if (small % 8 == 0) { push(8); small /= 8; }
-   if (small % 4 == 0) { push(4); small /= 4; }
-   if (small % 2 == 0) { push(2); small /= 2; }
-   while (small % 9 == 0) { push(9); small /= 9; }
-   for (int f = 3; f <= kAnyMaxFixedOdd; f += 2)
-      while (small % f == 0) { push(f); small /= f; }
-   return np;
-}
-} // namespace d2d
+// (the factorisation any_factorize lives in fft_any.cuh and is the one fft_any.cu calls: `big` selects the radix set of the
+// 128-thread build, radices up to 31 and the fused 20 / 24 / 30, or of the 256-thread build, radices up to 16)
 
-template <typename T> double run(int n)
+template <typename T> double run(int n, bool big)
 {
    using namespace d2d;
    using T2 = typename Vec2<T>::type;
    int radix[kMaxAnyPass];
-   const int np = factorize(n, radix, kMaxAnyPass);
+   const int np = any_factorize(n, radix, kMaxAnyPass, big, nullptr);
+   long long prod = 1;
+   for (int p = 0; p < np; p++) prod *= radix[p];
+   if (prod != n) { printf("n=%d: radices multiply to %lld\n", n, prod); return 1e30; }
    std::vector<T2> W(n), a(n), b(n);
    std::vector<double> xr(n), xi(n);
    const long double pi2 = 2 * 3.14159265358979323846264338327950288L;
@@ -54,18 +37,20 @@ template <typename T> double run(int n)
       bool fixed = true;
       for (int jj = 0; jj < M && fixed; jj++) {
          switch (R) {
-         case 2: any_bfly_fixed<T, 2>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 3: any_bfly_fixed<T, 3>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 4: any_bfly_fixed<T, 4>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 5: any_bfly_fixed<T, 5>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 7: any_bfly_fixed<T, 7>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 8: any_bfly_fixed<T, 8>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 9: any_bfly_fixed<T, 9>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 11: any_bfly_fixed<T, 11>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 13: any_bfly_fixed<T, 13>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         case 16: any_bfly_fixed<T, 16>(src, dst, W.data(), n, Ns, rNs, jj); break;
-         default: fixed = false;
+#define D2D_X(r) case r: any_bfly_fixed<T, r>(src, dst, W.data(), n, Ns, rNs, jj); break;
+            D2D_ANY_RADICES_SMALL(D2D_X)
+         default:
+            fixed = false;
          }
+         if (!fixed && big) {
+            fixed = true;
+            switch (R) {
+               D2D_ANY_RADICES_BIG(D2D_X)
+            default:
+               fixed = false;
+            }
+         }
+#undef D2D_X
       }
       if (!fixed) { // the kernel's run-time radix path: twiddle sweep, then one item per (butterfly, output pair)
          const int H = (R - 1) / 2;
@@ -92,7 +77,7 @@ template <typename T> double run(int n)
       err = fmax(err, fmax(fabs((double)(src[k].x - re)), fabs((double)(src[k].y - im))));
       mx = fmax(mx, fmax(fabs((double)re), fabs((double)im)));
    }
-   printf("n=%5d passes=%d [", n, np);
+   printf("n=%5d %s passes=%d [", n, big ? "big  " : "small", np);
    for (int p = 0; p < np; p++) printf("%d%s", radix[p], p + 1 < np ? "." : "");
    printf("] rel err %.2e\n", err / mx);
    return err / mx;
@@ -100,10 +85,12 @@ template <typename T> double run(int n)
 
 int main()
 {
-   const int sizes[] = {1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 17, 18, 20, 21, 22, 24, 26, 27, 34, 35, 48, 49, 51, 60, 66, 68, 81, 96, 100, 102, 121, 127, 130, 144, 210, 257, 289, 323, 360, 510, 768, 1000, 1001, 1536, 3000};
+   const int sizes[] = {1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 17, 18, 20, 21, 22, 24, 26, 27, 34, 35, 48, 49, 51, 60, 66, 68, 81, 96, 100, 102, 121, 127, 130, 144, 210, 257, 289, 323, 360, 375, 510, 544, 600, 625, 675, 768, 899, 961, 1000, 1001, 1331, 1536, 2187, 3000, 3125};
    double worst = 0, worst32 = 0;
-   for (int n : sizes) worst = fmax(worst, run<double>(n));
-   for (int n : sizes) worst32 = fmax(worst32, run<float>(n));
+   for (int big = 0; big < 2; big++) {
+      for (int n : sizes) worst = fmax(worst, run<double>(n, big != 0));
+      for (int n : sizes) worst32 = fmax(worst32, run<float>(n, big != 0));
+   }
    printf("worst fp64 %.2e, fp32 %.2e\n", worst, worst32);
    return (worst < 1e-13 && worst32 < 2e-5) ? 0 : 1;
 }
