@@ -23,8 +23,9 @@ struct RootKey {
 std::mutex g_root_mutex;
 std::map<RootKey, void *> g_roots;
 
-constexpr size_t kAnySmemBudget = 200 * 1024; // what the geometry may use
-constexpr size_t kAnySmemMax = 224 * 1024;    // opt-in limit of sm_100a (227 KB) minus the kernel's static shared memory (line tables)
+constexpr size_t kAnyLineBudget = 200 * 1024; // bounds the longest line of the shared-memory kernel (fft_any_max_n)
+constexpr size_t kAnySmemBudget = 210 * 1024; // what the geometry may use
+constexpr size_t kAnySmemMax = 220 * 1024;    // opt-in limit of sm_100a (227 KB) minus the kernel's static shared memory (6 KB of line tables)
 
 // W[k] = exp(-2 pi i k / n): octant-reduced so that every entry is accurate to the last bit or so
 const void *roots_for(int device, int n, int f64)
@@ -82,7 +83,7 @@ template <typename T, int MODE, bool BIG> cudaError_t launch_any_build(const Fft
    int dev = 0;
    if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return e0;
    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-   if (smem + 4096 > 48 * 1024 && !smem_set_of[dev]) { // the kernel also has ~3 KB of static shared memory (line tables)
+   if (smem + 8192 > 48 * 1024 && !smem_set_of[dev]) { // the kernel also has 6 KB of static shared memory (line tables)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnySmemMax);
       if (e != cudaSuccess) return e;
       smem_set_of[dev] = true;
@@ -144,7 +145,7 @@ void fft_any_release_all()
 }
 
 // largest transform length the shared-memory kernel takes (one line per block, two buffers + the root table)
-int fft_any_max_n(int f64) { return (int)(kAnySmemBudget / (3 * (size_t)(f64 ? 16 : 8))) - 1; }
+int fft_any_max_n(int f64) { return (int)(kAnyLineBudget / (3 * (size_t)(f64 ? 16 : 8))) - 1; }
 
 // geometry of one launch: lines per block (a power of two), shared-memory pitch, which axis the lanes follow on each side
 static size_t configure_any(FftArgsAny &ga, int f64, int mode, bool split_step)
@@ -162,22 +163,42 @@ static size_t configure_any(FftArgsAny &ga, int f64, int mode, bool split_step)
       if (mode == MODE_C2R) ga.out_fast_a = (g.rsa == 1 && g.rse != 1);
       else ga.out_fast_a = (g.out.sa[0] == 1 && g.out.se[0] != 1);
    }
+   // The input of the next group of lines is prefetched with cp.async into a third line buffer while the current group runs
+   // its passes (plain c2c stages and r2c; D2D_ANY_ASYNC=0 turns it off): ncu showed the two-buffer kernel waiting for its
+   // global loads 33-52 % of the time (profiles/r02_k_ncu_any510.txt).
+   static const int async_enabled = getenv("D2D_ANY_ASYNC") ? atoi(getenv("D2D_ANY_ASYNC")) : 1;
+   const bool can_async = async_enabled && !split_step && (mode == MODE_C2C || mode == MODE_R2C);
    // lines per block (a power of two): 128-byte rows when lines are strided, about 2048 elements of work per block,
    // within the shared-memory budget; narrower (never below the row width) when that lets two blocks share an SM
-   auto smem_of = [&](int lines) { return ces * ((size_t)n + 2 * (size_t)lines * ga.pitch); };
    auto pow2_ceil = [](long long v) { int l = 0; while ((1LL << l) < v) l++; return l; };
    static const int row_bytes = getenv("D2D_ANY_ROW_BYTES") ? atoi(getenv("D2D_ANY_ROW_BYTES")) : 128; // experiments: 64 halves the tile
+   static const int min_row_bytes = getenv("D2D_ANY_MIN_ROW_BYTES") ? atoi(getenv("D2D_ANY_MIN_ROW_BYTES")) : 64; // experiments
    const int want_rows_log2 = pow2_ceil((long long)(std::max(16, row_bytes) / (int)ces));
-   int ll = std::max(want_rows_log2, pow2_ceil((2048 + n - 1) / n));
-   ll = std::min(ll, pow2_ceil(max_lines));
-   ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
-   while (ll > 0 && smem_of(1 << ll) > kAnySmemBudget) ll--;
-   // two blocks per SM (one loads / stores while the other computes) are worth more than 128-byte rows: 510^3 pair 14.4 ->
-   // 11.4 ms with 64-byte rows (profiles/r01_l_any_and_transposes.txt)
-   const int min_rows_log2 = pow2_ceil((long long)(64 / ces));
-   while (ll > min_rows_log2 && smem_of(1 << ll) > 110 * 1024) ll--;
-   ga.lines_log2 = ll;
-   return smem_of(1 << ll);
+   const int min_rows_log2 = pow2_ceil((long long)(std::max<int>(min_row_bytes, (int)ces) / (int)ces));
+   auto pick = [&](int nbuf, int &ll) {
+      auto smem_of = [&](int lines) { return ces * ((size_t)n + (size_t)nbuf * (size_t)lines * ga.pitch); };
+      ll = std::max(want_rows_log2, pow2_ceil((2048 + n - 1) / n));
+      ll = std::min(ll, pow2_ceil(max_lines));
+      ll = std::min(ll, pow2_ceil((long long)g.na * g.nb));
+      while (ll > 0 && smem_of(1 << ll) > kAnySmemBudget) ll--;
+      // two blocks per SM (one loads / stores while the other computes) are worth more than 128-byte rows: 510^3 pair 14.4 ->
+      // 11.4 ms with 64-byte rows (profiles/r01_l_any_and_transposes.txt)
+      while (ll > min_rows_log2 && smem_of(1 << ll) > 108 * 1024) ll--;
+      return smem_of(1 << ll);
+   };
+   int ll2 = 0, ll3 = 0;
+   const size_t s2 = pick(2, ll2);
+   size_t s3 = 0;
+   // three buffers when the line still fits; a block that then has the SM to itself keeps its rows as wide as two buffers allow
+   bool use3 = false;
+   if (can_async) {
+      s3 = pick(3, ll3);
+      use3 = s3 <= kAnySmemBudget && ll3 >= std::min(ll2, min_rows_log2);
+   }
+   ga.nbuf = use3 ? 3 : 2;
+   ga.async_in = use3 ? 1 : 0;
+   ga.lines_log2 = use3 ? ll3 : ll2;
+   return use3 ? s3 : s2;
 }
 
 // Lengths beyond the shared-memory kernel (n > fft_any_max_n): n = n1 n2 with both factors within its reach, as TWO launches of

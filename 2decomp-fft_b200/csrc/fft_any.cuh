@@ -145,6 +145,8 @@ struct FftArgsAny {
    int npass;
    int radix[kMaxAnyPass];
    int big;                   // 1: the build with radices up to 31 in 128 threads runs it
+   int nbuf;                  // line buffers in shared memory: 2, or 3 when the next group's input is prefetched (async_in)
+   int async_in;              // 1: the input of group i+1 lands with cp.async in the third buffer while group i runs its passes
    int lines_log2;            // complex lines per block = 1 << lines_log2
    int pitch;                 // shared-memory pitch of a line, in complex elements (odd)
    int in_fast_a, out_fast_a; // 1: adjacent lines (axis a) are contiguous in global memory on that side
@@ -292,10 +294,10 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
    const int nh = n / 2 + 1;
    extern __shared__ __align__(16) unsigned char any_smem[];
    T2 *W = reinterpret_cast<T2 *>(any_smem);
-   T2 *buf0 = W + n;
-   T2 *buf1 = buf0 + (size_t)L * pitch;
-   __shared__ int line_a[kAnyMaxLines], line_b[kAnyMaxLines]; // (a, b) of the block's lines; a = -1: beyond the batch
-   __shared__ int line_sub[kAnyMaxLines];                     // split steps: the sub-index of the virtual batch index
+   T2 *const bufs[3] = {W + n, W + n + (size_t)L * pitch, W + n + 2 * (size_t)L * pitch}; // [2] exists when ga.nbuf == 3
+   // (a, b) of the block's lines; a = -1: beyond the batch; sub: split steps, the sub-index of the virtual batch index.
+   // Two sets: the prefetch of group i+1 fills the other one while group i still needs its own for the stores.
+   __shared__ int line_a_[2][kAnyMaxLines], line_b_[2][kAnyMaxLines], line_sub_[2][kAnyMaxLines];
    const int split = (MODE == MODE_C2C && ga.split > 1) ? ga.split : 1;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = kThreads / 32;
@@ -309,10 +311,9 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
    const long long total = (long long)g.na * g.nb; // complex lines (pairs of real lines for r2c / c2r)
    const long long ngroups = (total + L - 1) >> LL;
    const bool bw = g.backward != 0;
-   T2 *const my0 = buf0 + pl * pitch, *const my1 = buf1 + pl * pitch;
+   const bool async = (MODE != MODE_C2R) && ga.async_in != 0 && ga.nbuf == 3 && split == 1;
 
-   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-      __syncthreads(); // W is staged; the previous group's stores have read the buffers and the line table
+   auto fill_table = [&](long long grp, int par) {
       if (tid < L) {
          const long long id = (grp << LL) + tid;
          int a = -1, b = 0, sub = 0;
@@ -324,25 +325,122 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
                a /= split;
             }
          }
-         line_a[tid] = a;
-         line_b[tid] = b;
-         line_sub[tid] = sub;
+         line_a_[par][tid] = a;
+         line_b_[par][tid] = b;
+         line_sub_[par][tid] = sub;
       }
+   };
+   // fast_a: lanes run over the lines first (l = i mod L); otherwise one warp walks along a line
+   auto for_each = [&](int len, bool fast_a, auto &&fn) {
+      if (fast_a) {
+         const int items = len << LL;
+         for (int i = tid; i < items; i += kThreads) fn(i & (L - 1), i >> LL);
+      } else {
+         for (int l = warp; l < L; l += NW)
+            for (int e = lane; e < len; e += 32) fn(l, e);
+      }
+   };
+   // cp.async (LDGSTS) of one group's input straight into a line buffer: C2C elements as they are (the conjugation of a
+   // backward transform happens in shared memory afterwards), R2C the two real lines of a pair into the two halves
+   auto issue_async = [&](T2 *dstbuf, int par) {
+      const int *la = line_a_[par], *lb = line_b_[par];
+      if constexpr (MODE == MODE_C2C) {
+         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            const int a = la[l];
+            T2 *d = &dstbuf[l * pitch + e];
+            if (a >= 0) {
+               int pc;
+               const long long off = piece_addr(g.in, e, a, lb[l], pc);
+               cp_async<sizeof(T2)>(d, reinterpret_cast<const T2 *>(g.in.ptr[pc]) + off);
+            } else {
+               *d = T2{0, 0};
+            }
+         });
+      } else if constexpr (MODE == MODE_R2C) {
+         const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
+         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            const int a = la[l];
+            T2 *d = &dstbuf[l * pitch + e];
+            if (a >= 0) {
+               const long long off = (long long)e * g.rse + (2LL * a) * g.rsa + (long long)lb[l] * g.rsb;
+               cp_async<sizeof(T)>(&d->x, rp + off);
+               if (2 * a + 1 < g.na_real) cp_async<sizeof(T)>(&d->y, rp + off + g.rsa);
+               else d->y = 0;
+            } else {
+               *d = T2{0, 0};
+            }
+         });
+      }
+      cp_async_commit();
+   };
+
+   long long grp = blockIdx.x;
+   int cur = 0, par = 0; // bufs[cur] holds / receives the input of the current group; par: its set of line tables
+   if (async && grp < ngroups) {
+      fill_table(grp, 0);
+      __syncthreads();
+      issue_async(bufs[0], 0);
+   }
+   for (; grp < ngroups; grp += gridDim.x, par ^= 1) {
+      T2 *const buf0 = bufs[cur], *const buf1 = bufs[cur + 1 < ga.nbuf ? cur + 1 : cur + 1 - ga.nbuf];
+      T2 *const my0 = buf0 + pl * pitch, *const my1 = buf1 + pl * pitch;
+      const int *line_a = line_a_[par], *line_b = line_b_[par], *line_sub = line_sub_[par];
+      if (async) {
+         cp_async_wait_all();
+         __syncthreads(); // this group's input has landed (and W); the previous group's stores have read their buffer
+         const long long nxt = grp + gridDim.x;
+         if (nxt < ngroups) {
+            fill_table(nxt, par ^ 1);
+            __syncthreads();
+            issue_async(bufs[(cur + 2) % 3], par ^ 1);
+         }
+         // (a backward c2c needs no conjugation here: its input lands as it is and the stores read the result of the
+         // forward passes in reversed order, X_b[k] = X_f[(n - k) mod n])
+      } else {
+      __syncthreads(); // W is staged; the previous group's stores have read the buffers and the line table
+      fill_table(grp, par);
       __syncthreads();
       // ------------------------------------------------------------------ load -> buf0
-      // fast_a: lanes run over the lines first (l = i mod L); otherwise one warp walks along a line
-      auto for_each = [&](int len, bool fast_a, auto &&fn) {
+      // Global loads are batched: a thread issues U independent loads before it touches shared memory.  One load per loop
+      // trip (the first version of this kernel) left ~8 KB in flight per SM and bounded the whole kernel by memory latency.
+      auto for_each_ld = [&](int len, bool fast_a, auto &&ld, auto &&st) {
+         constexpr int U = ((MODE == MODE_C2R) ? 4 : 8) * (BIG ? 2 : 1) / (sizeof(T) == 8 ? 2 : 1); // ~32 KB in flight per SM
+         using Item = decltype(ld(0, 0));
          if (fast_a) {
             const int items = len << LL;
-            for (int i = tid; i < items; i += kThreads) fn(i & (L - 1), i >> LL);
+            for (int i0 = tid; i0 < items; i0 += U * kThreads) {
+               Item v[U];
+#pragma unroll
+               for (int u = 0; u < U; u++) {
+                  const int i = i0 + u * kThreads;
+                  if (i < items) v[u] = ld(i & (L - 1), i >> LL);
+               }
+#pragma unroll
+               for (int u = 0; u < U; u++) {
+                  const int i = i0 + u * kThreads;
+                  if (i < items) st(i & (L - 1), i >> LL, v[u]);
+               }
+            }
          } else {
             for (int l = warp; l < L; l += NW)
-               for (int e = lane; e < len; e += 32) fn(l, e);
+               for (int e0 = lane; e0 < len; e0 += 32 * U) {
+                  Item v[U];
+#pragma unroll
+                  for (int u = 0; u < U; u++)
+                     if (e0 + 32 * u < len) v[u] = ld(l, e0 + 32 * u);
+#pragma unroll
+                  for (int u = 0; u < U; u++)
+                     if (e0 + 32 * u < len) st(l, e0 + 32 * u, v[u]);
+               }
          }
       };
+      struct Pair2 {
+         T2 A, B;
+      };
       if constexpr (MODE == MODE_C2C) {
+         auto put = [&](int l, int e, T2 x) { buf0[l * pitch + e] = x; };
          if (split > 1) { // a step of a two-kernel transform
-            for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            for_each_ld(n, ga.in_fast_a != 0, [&](int l, int e) {
                const int a = line_a[l];
                T2 x = T2{0, 0};
                if (a >= 0) {
@@ -358,22 +456,22 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
                   }
                   if (bw) x.y = -x.y;
                }
-               buf0[l * pitch + e] = x;
-            });
+               return x;
+            }, put);
          } else {
-            for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+            for_each_ld(n, ga.in_fast_a != 0, [&](int l, int e) {
                const int a = line_a[l];
                T2 x = T2{0, 0};
                if (a >= 0) {
                   x = load_piece<T2>(g.in, e, a, line_b[l]);
                   if (bw) x.y = -x.y;
                }
-               buf0[l * pitch + e] = x;
-            });
+               return x;
+            }, put);
          }
       } else if constexpr (MODE == MODE_R2C) {
          const T *__restrict__ rp = reinterpret_cast<const T *>(g.rptr);
-         for_each(n, ga.in_fast_a != 0, [&](int l, int e) {
+         for_each_ld(n, ga.in_fast_a != 0, [&](int l, int e) {
             const int a = line_a[l];
             T2 x = T2{0, 0};
             if (a >= 0) {
@@ -381,16 +479,19 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
                x.x = rp[off];
                if (2 * a + 1 < g.na_real) x.y = rp[off + g.rsa];
             }
-            buf0[l * pitch + e] = x;
-         });
+            return x;
+         }, [&](int l, int e, T2 x) { buf0[l * pitch + e] = x; });
       } else { // C2R: Z[k] = A[k] + i B[k], Z[n-k] = conj(A[k]) + i conj(B[k]); the forward passes get conj(Z)
-         for_each(nh, ga.in_fast_a != 0, [&](int l, int k) {
+         for_each_ld(nh, ga.in_fast_a != 0, [&](int l, int k) {
             const int a = line_a[l];
-            T2 A = T2{0, 0}, B = T2{0, 0};
+            Pair2 v{T2{0, 0}, T2{0, 0}};
             if (a >= 0) {
-               A = load_piece<T2>(g.in, k, 2LL * a, line_b[l]);
-               if (2 * a + 1 < g.na_real) B = load_piece<T2>(g.in, k, 2LL * a + 1, line_b[l]);
+               v.A = load_piece<T2>(g.in, k, 2LL * a, line_b[l]);
+               if (2 * a + 1 < g.na_real) v.B = load_piece<T2>(g.in, k, 2LL * a + 1, line_b[l]);
             }
+            return v;
+         }, [&](int l, int k, Pair2 v) {
+            T2 A = v.A, B = v.B;
             const bool selfconj = (k == 0) || (2 * k == n);
             if (selfconj) { A.y = 0; B.y = 0; }
             buf0[l * pitch + k] = T2{A.x - B.y, -(A.y + B.x)};
@@ -398,6 +499,7 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
          });
       }
       __syncthreads();
+      } // synchronous load
 
       // ------------------------------------------------------------------ passes (ping-pong), line pl, thread pt of TL
       T2 *src = my0, *dst = my1;
@@ -448,6 +550,7 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
       T2 *const res = src - pl * pitch; // block view of the buffer holding the result
 
       // ------------------------------------------------------------------ store
+      if (async) cur = (cur + 2) % 3; // the prefetched buffer becomes the input of the next group
       if (g.debug & 1) continue;
       if constexpr (MODE == MODE_C2C) {
          if (split > 1) {
@@ -468,11 +571,12 @@ __global__ void __launch_bounds__(BIG ? kAnyThreadsBig : kAnyThreads, 2) fft_any
                }
             });
          } else {
+            const bool rev = bw && async && !g.passthrough; // prefetched input was not conjugated: index reversal instead of conj . forward . conj
             for_each(n, ga.out_fast_a != 0, [&](int l, int e) {
                const int a = line_a[l];
                if (a >= 0) {
-                  T2 x = res[l * pitch + e];
-                  if (bw) x.y = -x.y;
+                  T2 x = res[l * pitch + ((rev && e) ? n - e : e)];
+                  if (bw && !async) x.y = -x.y; // the synchronous loads conjugated the input
                   store_piece<T2>(g.out, e, a, line_b[l], x);
                }
             });
