@@ -384,3 +384,55 @@ def test_overlapped_chain_matches_oracle(shape, grid, fmt, monkeypatch):
             assert np.max(np.abs(res[r][2] - ref_c[r])) / cmax < 1e-12, ("c2c", r)
     rt = orc.gather([x[1] for x in res], shape, grid, pin) / np.prod(shape)
     assert np.max(np.abs(rt - g)) < 1e-13
+
+
+@pytest.mark.parametrize("grid", [(8, 1), (1, 8), (8, 2)])
+def test_process_grid_sides_at_the_cap(grid):
+    """the widest process-grid side the library takes (8 ranks per communicator = kMaxPieces pieces per line): transposes
+    bit-exact and r2c / c2r against the oracle on a grid whose pencils are ragged (34 / 8, 18 / 8 spectral planes)."""
+    import torch
+    p = pkg()
+    shape = (34, 40, 24)
+    nranks = grid[0] * grid[1]
+    g = _index_field(shape, np.float64)
+    want = [orc.scatter(g, grid, pen) for pen in range(3)]
+    rng = np.random.default_rng(8)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    ins = orc.scatter(f, grid, 0)
+    ref = orc.fft_3d_r2c_world(shape, grid, orc.PHYSICAL_IN_X, ins)
+
+    def body(rank, group):
+        d2d = p.Decomp2d(*shape, grid[0], grid[1], rank=rank, nranks=nranks, group=group, device=0)
+        u1, u2, u3 = d2d.alloc_x(torch.float64), d2d.alloc_y(torch.float64), d2d.alloc_z(torch.float64)
+        u1.copy_(torch.from_numpy(want[0][rank]))
+        d2d.transpose_x_to_y(u1, u2)
+        d2d.transpose_y_to_z(u2, u3)
+        ok = np.array_equal(u2.cpu().numpy(), want[1][rank]) and np.array_equal(u3.cpu().numpy(), want[2][rank])
+        eng = p.Decomp2dFFTEngine(d2d, p.PHYSICAL_IN_X)
+        in_r, out_c = d2d.alloc_x(torch.float64, eng.ph), d2d.alloc_z(torch.complex128, eng.sp)
+        in_r.copy_(torch.from_numpy(ins[rank]))
+        eng.fft_3d(in_r, out_c)
+        spec = out_c.cpu().numpy()
+        back = d2d.alloc_x(torch.float64, eng.ph)
+        eng.fft_3d(out_c, back)
+        res = (ok, spec, back.cpu().numpy())
+        eng.fin()
+        d2d.finalize()
+        return res
+
+    res = run_ranks(nranks, body)
+    assert all(r[0] for r in res), "transposes"
+    smax = max(np.max(np.abs(s)) for s in ref if s.size)
+    for r in range(nranks):
+        if ref[r].size:
+            assert np.max(np.abs(res[r][1] - ref[r])) / smax < 1e-12, r
+    rt = orc.gather([x[2] for x in res], shape, grid, 0) / np.prod(shape)
+    assert np.max(np.abs(rt - f)) < 1e-13
+
+
+def test_process_grid_side_beyond_the_cap_is_rejected():
+    p = pkg()
+    grp = p.Group(9)
+    with pytest.raises(p.Decomp2dError, match="larger than 8"):
+        p.Decomp2d(64, 64, 64, 9, 1, rank=0, nranks=9, group=grp, device=0)
+    grp.destroy()
