@@ -32,9 +32,11 @@ def main():
     grids = {1: [(1, 1)], 2: [(1, 2), (2, 1)], 4: [(2, 2), (1, 4), (4, 1)], 8: [(2, 4), (4, 2)]}[world]
     if len(sys.argv) > 2:
         grids = [(int(sys.argv[1]), int(sys.argv[2]))]
-    shapes = ((32, 16, 64), (256, 64, 512), (64, 256, 32))
+    # powers of two (cp.async and TMA kernels), 3 * 2^k / 5 * 2^k (compiled mixed-radix plans), the reference's default
+    # 17 x 13 x 11 type (any-length kernel with prefetch)
+    shapes = ((32, 16, 64), (256, 64, 512), (64, 256, 32), (384, 40, 320), (34, 26, 22))
     if os.environ.get("MGPU_SHAPES") == "small":
-        shapes = ((32, 16, 64), (64, 256, 32))
+        shapes = ((32, 16, 64), (64, 256, 32), (34, 26, 22))
     worst = 0.0
     nfail = 0
     for grid in grids:
