@@ -85,7 +85,8 @@ def test_test2d_transposes_exact(shape, grid, dtype):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 13, 16, 17, 34, 51, 64, 100, 128, 256, 1000, 1024, 1025])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 13, 16, 17, 34, 51, 64, 100, 128, 256, 1000, 1024, 1025,
+                               6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 10, 20, 40, 80, 160, 320, 640, 1280, 510])  # + the compiled 3*2^k / 5*2^k lengths
 @pytest.mark.parametrize("isign", [-1, 1])
 def test_spcfft_vs_pocketfft(n, isign):
     """SPCFFT (glassman.f90:29-108) is an unnormalised DFT with exp(isign 2 pi i jk/n)."""
