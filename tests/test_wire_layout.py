@@ -38,7 +38,7 @@ def offsets(m, e, a, b):
 
 
 @pytest.mark.parametrize("padq", [8, 16, 1])
-@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (3, 2), (4, 2)])
+@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (3, 2), (4, 2), (8, 1), (1, 8)])
 @pytest.mark.parametrize("shape", [(17, 13, 11), (32, 16, 33), (9, 24, 16)])
 @pytest.mark.parametrize("link", [(0, 1), (1, 0), (1, 2), (2, 1)])
 def test_link_maps_compose_to_the_reference_transpose(shape, grid, link, padq):
