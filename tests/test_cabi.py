@@ -93,3 +93,38 @@ def test_even_counts_match_oracle_and_formula(shape, grid):
         # a padded buffer holds every real block
         assert max(d.x1cnts) <= d.x1count and max(d.y1cnts) <= d.y1count and max(d.y2cnts) <= d.y2count and max(d.z2cnts) <= d.z2count
         d.finalize()
+
+
+def test_fortran_shim_binds_only_declared_symbols():
+    """the ISO_C_BINDING interfaces of 2decomp-fft_b200/fortran/*.f90 (source only: no Fortran compiler in this image) must
+    name entry points that include/d2d_b200.h declares and the library exports, and cover the calls of the hot path"""
+    p = pkg()
+    lib = p.lib()
+    hdr = open(os.path.join(ROOT, "include", "d2d_b200.h")).read()
+    declared = set(re.findall(r"\b(d2d_[a-z0-9_]+)\s*\(", hdr))
+    bound = set()
+    fdir = os.path.join(ROOT, "2decomp-fft_b200", "fortran")
+    for f in os.listdir(fdir):
+        if f.endswith(".f90"):
+            bound |= set(re.findall(r'bind\(C,\s*name\s*=\s*"([a-z0-9_]+)"\)', open(os.path.join(fdir, f)).read(), flags=re.I))
+    assert len(bound) >= 25
+    assert not (bound - declared), sorted(bound - declared)
+    assert all(hasattr(lib, n) for n in bound)
+    for needed in ("d2d_ctx_create_bootstrap", "d2d_decomp_create", "d2d_transpose", "d2d_fft_plan_create", "d2d_fft_3d_r2c", "d2d_fft_3d_c2r",
+                   "d2d_fft_3d_c2c", "d2d_halo_update", "d2d_last_error"):
+        assert needed in bound, needed
+
+
+def test_kernel_registry_covers_mixed_radix_sizes():
+    """compiled plans for 3 * 2^k and 5 * 2^k (csrc/fft_kernel.cuh): every mode, both precisions"""
+    p = pkg()
+    lib = p.lib()
+    buf = ctypes.create_string_buffer(256)
+    desc = []
+    for i in range(lib.d2d_fft_kernel_count()):
+        assert lib.d2d_fft_kernel_describe(i, buf, 256) == 0
+        desc.append(buf.value.decode())
+    for size in (6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 10, 20, 40, 80, 160, 320, 640, 1280):
+        for ty in ("f64", "f32"):
+            for mode in ("c2c", "r2c", "c2r"):
+                assert any(d.startswith(f"n={size} {ty} tile {mode}") for d in desc), (size, ty, mode)
